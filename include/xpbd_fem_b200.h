@@ -1,0 +1,201 @@
+/*
+ * xpbd_fem_b200.h — C ABI of the B200-native small-step XPBD tet solver.
+ *
+ * Drop-in boundary for the reference's `Geo` interface on the linear-tet path
+ * (reference = jak-xyz/xpbd-fem, paths below relative to XPBDFEM/):
+ *
+ *   reference                                              this library
+ *   ------------------------------------------------------ ------------------------------
+ *   GenerateBlock(Element_T4, ...)        MeshGen.cpp:246   xf_generate_tet_block
+ *   GeoLinear3d::Init                     Geo.cpp:697       xf_create
+ *   Geo::Substep (Geo3d::Substep)         Geo.h:21, Geo.cpp:305   xf_substep
+ *   Geo::Transform                        Geo.h:22, Geo.cpp:358   xf_transform
+ *   Geo::CalculateVolume                  Geo.h:28, Geo.cpp:827   xf_volume
+ *   Geo::VertCount / ElementCount         Geo.h:29-30       xf_vert_count / xf_element_count
+ *   public members X, V, w, X0, O, flags  Geo.h:61-66       xf_get_state / xf_set_state / xf_get_rest
+ *   public member tOrder                  Geo.h:161         xf_get_order (the schedule's equivalent serial order)
+ *   Settings POD                          Settings.h:79-102 xf_settings (byte-identical, 160 B)
+ *   Manipulator POD                       Manipulator.h:9-13 xf_manipulator (flat floats)
+ *   wasm C exports (precedent for a flat C ABI)  wasm/main.cpp:8-17
+ *
+ * All entry points are plain C: pointers, sizes, PODs.  No C++ or torch types cross the boundary.
+ * Every function returns 0 on success or a negative xf_status; xf_last_error() gives the message of
+ * the calling thread's last failure.  The library never falls back to a CPU path: without a CUDA
+ * device every compute entry point fails with XF_ERR_CUDA.
+ *
+ * Threading: one host thread per scene at a time.  Device work is enqueued on the scene's stream
+ * (library-owned unless xf_create_params.stream is given); xf_substep is asynchronous, the state
+ * getters synchronise.
+ */
+#ifndef XPBD_FEM_B200_H
+#define XPBD_FEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XF_ABI_VERSION 1
+
+typedef enum xf_status {
+	XF_OK = 0,
+	XF_ERR_INVALID = -1,     /* bad argument / malformed mesh stream */
+	XF_ERR_CUDA = -2,        /* CUDA runtime failure (message has the CUDA error string) */
+	XF_ERR_UNSUPPORTED = -3, /* settings select something outside the tet hot path */
+	XF_ERR_NOMEM = -4,
+	XF_ERR_COLORING = -5     /* supplied colouring is not conflict-free, or too many colours */
+} xf_status;
+
+/* ---- flag word, identical to Settings.h:9-75 ---- */
+#define XF_SETTINGS_ENERGY_BIT 6
+#define XF_SETTINGS_ENERGY_MASK 31u
+#define XF_SETTINGS_XPBD_SOLVE_BIT 11
+#define XF_SETTINGS_RAYLEIGH_TYPE_BIT 20
+#define XF_SETTINGS_RAYLEIGH_TYPE_MASK 3u
+#define XF_SETTINGS_LOCK_LEFT (1u << 26)
+#define XF_SETTINGS_LOCK_RIGHT (1u << 27)
+#define XF_ELEMENT_T4 5u
+#define XF_ENERGY_MIXED 3u
+#define XF_ENERGY_MIXED_SEL 4u
+#define XF_ENERGY_YEOH_SKIN 5u
+#define XF_ENERGY_YEOH_SKIN_FAST 7u
+#define XF_PATTERN_UNIFORM 0u
+#define XF_PATTERN_MIRRORED 1u
+#define XF_RAYLEIGH_PAPER 0u
+#define XF_RAYLEIGH_LIMIT 1u
+#define XF_RAYLEIGH_POST 2u
+#define XF_RAYLEIGH_POST_AMORTIZED 3u
+#define XF_AMORTIZATION_PERIOD 8u
+/* per-vertex flags, Geo.h:16-20 */
+#define XF_VERT_LEFT 1u
+#define XF_VERT_RIGHT 2u
+#define XF_VERT_PICKABLE 16u
+
+/* Byte-identical to the reference's `struct Settings` (Settings.h:79-102; sizeof == 160, align 16). */
+typedef struct xf_settings {
+	float timeScale;
+	float substepsPerSecond;
+	uint32_t volumePasses;
+	uint32_t _pad0;
+	float gravity[2];
+	float compliance;
+	float damping;
+	float pbdDamping;
+	float drag;
+	float poissonsRatio;
+	float wonkiness;
+	float leftRightSeparation;
+	uint32_t flags;
+	float areaAndTimeCorrectedPbdDamping;
+	float volumeAndTimeCorrectedPbdDamping;
+	float amortizedAreaAndTimeCorrectedPbdDamping;
+	float amortizedVolumeAndTimeCorrectedPbdDamping;
+	float timeCorrectedDrag;
+	uint32_t _pad1;
+	float lockedRightTransform[4];    /* mat2, column-major */
+	float lockedRightTransform3d[12]; /* mat3, column-major, each column padded to 16 B */
+	uint32_t tickId;
+	uint32_t _pad2[3];
+} xf_settings;
+
+/* Flat mirror of Manipulator.h:9-13.  picked != 0 <=> `manip.pickedGeo == this` (Geo.cpp:334). */
+typedef struct xf_manipulator {
+	float pos[3], manipPlaneNormal[3], pick0[3], pickDir[3], pickDirOld[3], pickDirTarget[3];
+	int32_t picked;
+	uint32_t pickedPointIdx;
+} xf_manipulator;
+
+typedef enum xf_precision {
+	XF_PRECISION_EXACT = 0, /* every fp32 operation rounded separately, IEEE division: bit-identical to the
+	                           reference built with -ffp-contract=off */
+	XF_PRECISION_FAST = 1   /* same formulas, FMA contraction and prefactored constants recomputed in registers */
+} xf_precision;
+
+typedef enum xf_schedule {
+	XF_SCHEDULE_AUTO = 0,
+	XF_SCHEDULE_LAUNCH_PER_COLOR = 1, /* one kernel launch per colour (CUDA-graph replayed) */
+	XF_SCHEDULE_PERSISTENT = 2        /* one cooperative launch per xf_substep call, grid barriers between colours */
+} xf_schedule;
+
+typedef struct xf_create_params {
+	uint32_t abiVersion;   /* XF_ABI_VERSION */
+	int32_t device;        /* CUDA device ordinal */
+	float density;         /* Sim::AddBlock passes 1.0f, 2.0f for the Armadillo (Demo.cpp:123) */
+	int32_t autoResize;    /* GeoLinear3d::Init's autoResize (Geo.cpp:726-728) */
+	int32_t precision;     /* xf_precision */
+	int32_t schedule;      /* xf_schedule */
+	void* stream;          /* cudaStream_t to enqueue on, or NULL for a library-owned stream */
+	const uint32_t* colorHint; /* optional: colour per element (in stream order); validated, never trusted */
+	uint32_t colorHintCount;   /* number of entries in colorHint (must equal the element count) */
+	uint32_t _reserved[5];
+} xf_create_params;
+
+typedef struct xf_scene xf_scene;
+
+const char* xf_last_error(void);
+int xf_device_count(int* outCount);
+void xf_default_create_params(xf_create_params* p);
+
+/* ---- mesh producer (host only; MeshGen.cpp:156-244) ----
+ * nodes: 3*(w+1)(h+1)(d+1) floats; idxStream: 30*w*h*d u32 in the reference's stream format
+ * [4, v0, v1, v2, v3]*; colorHint (optional, may be NULL): 6*w*h*d entries, an analytic
+ * 24-colouring for XF_PATTERN_UNIFORM (0xffffffff everywhere for other patterns). */
+int xf_generate_tet_block(uint32_t width, uint32_t height, uint32_t depth, float sx, float sy, float sz, uint32_t pattern,
+                          float wonkiness, float* nodes, uint32_t* idxStream, uint32_t* colorHint);
+
+/* ---- scene lifetime (GeoLinear3d::Init, Geo.cpp:697-772) ---- */
+int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream,
+              uint32_t idxCount, xf_scene** outScene);
+int xf_destroy(xf_scene* scene);
+
+uint32_t xf_vert_count(const xf_scene* scene);
+uint32_t xf_element_count(const xf_scene* scene);
+uint32_t xf_color_count(const xf_scene* scene);
+/* The serial element order the device schedule is equivalent to (inject into GeoLinear3d::tOrder). */
+int xf_get_order(const xf_scene* scene, uint32_t* order);
+int xf_get_colors(const xf_scene* scene, uint32_t* colorOfElement);
+/* Per-element constants as InitFiniteElement produced them (Fem.cpp:196-224); any pointer may be NULL. */
+int xf_get_elements(const xf_scene* scene, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea);
+
+/* ---- stepping (Geo3d::Substep, Geo.cpp:305-356), n substeps with tickId advancing per substep ---- */
+int xf_substep(xf_scene* scene, const xf_settings* settings, const xf_manipulator* manip, float dt, uint32_t n);
+int xf_sync(xf_scene* scene);
+
+/* Extensions named by the task that the reference lacks (semantics in DESIGN.md §Extensions). */
+int xf_set_ground(xf_scene* scene, int enabled, float y0, float friction);
+int xf_set_handles(xf_scene* scene, uint32_t count, const uint32_t* vertIdx, const float* targetXYZ);
+
+/* ---- state (host buffers, packed xyz triples of doubles like dvec3 without its padding) ---- */
+int xf_get_state(xf_scene* scene, double* X, double* V, float* w);
+int xf_set_state(xf_scene* scene, const double* X, const double* V, const float* w);
+int xf_get_rest(xf_scene* scene, double* X0, double* O, uint8_t* flags);
+int xf_get_origin(const xf_scene* scene, float* origin3);
+/* Asynchronous variants for pinned host buffers (e2e loop): enqueue on the scene's stream, no sync. */
+int xf_get_state_async(xf_scene* scene, double* X, double* V);
+int xf_set_state_async(xf_scene* scene, const double* X, const double* V);
+
+int xf_transform(xf_scene* scene, const float* m9 /* column-major mat3 */);
+/* fp32 sum in element order, bit-identical to GeoLinear3d::CalculateVolume (per-element terms on the device). */
+int xf_volume(xf_scene* scene, float* outVolume);
+
+/* Device-side statistics (fp64 reductions): [0] volume, [1] kinetic energy, [2] gravitational potential,
+ * [3] deviatoric elastic energy, [4] volumetric elastic energy, [5] count of non-finite position components. */
+int xf_stats(xf_scene* scene, const xf_settings* settings, double* out6);
+
+/* Introspection for benchmarks. */
+typedef struct xf_info {
+	uint32_t vertCount, elementCount, colorCount, minColorSize, maxColorSize;
+	uint32_t smCount, gridBlocks, blockThreads;
+	uint32_t elementRecordBytes; /* bytes streamed per element per sweep in the active precision */
+	uint32_t schedule;           /* resolved xf_schedule */
+	uint64_t kernelLaunches;     /* kernels launched by this scene so far */
+	uint64_t l2Bytes;            /* cudaDeviceProp::l2CacheSize */
+} xf_info;
+int xf_get_info(const xf_scene* scene, xf_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XPBD_FEM_B200_H */

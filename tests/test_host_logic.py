@@ -1,0 +1,163 @@
+"""CPU-only tests of the product's host side through the C ABI: the library loads and exports every
+declared symbol, element init / masses / flags are bit-identical to the reference, the colouring is
+conflict-free, and errors are reported the way the header promises.  No device compute is invoked:
+scenes are created host-only (device = -1), which can be inspected but never stepped."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from __graft_entry__ import ROOT, build, load_package
+from oracle import bindings as ob
+
+build()
+xf = load_package()
+
+
+def host_scene(nodes, idx, **kw):
+    return xf.GeoLinear3dCuda(nodes, idx, device=-1, **kw)
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "xpbd_fem_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|uint32_t|void|const char\*)\s+(xf_[a-z_0-9]+)\(", header, flags=re.M))
+    assert len(declared) >= 20
+    L = C.CDLL(xf.LIB_PATH)
+    missing = [n for n in sorted(declared) if not hasattr(L, n)]
+    assert not missing, missing
+    assert declared == set(xf.EXPORTS)
+
+
+def test_settings_pod_layout_matches_reference_offsets():
+    # offsets probed from the reference's own struct (Settings.h:79-102): see SURVEY §8a a1
+    S = xf.Settings
+    assert C.sizeof(S) == 160
+    expect = dict(timeScale=0, substepsPerSecond=4, volumePasses=8, gravity=16, compliance=24, damping=28, pbdDamping=32, drag=36,
+                  poissonsRatio=40, wonkiness=44, leftRightSeparation=48, flags=52, areaAndTimeCorrectedPbdDamping=56,
+                  volumeAndTimeCorrectedPbdDamping=60, amortizedAreaAndTimeCorrectedPbdDamping=64,
+                  amortizedVolumeAndTimeCorrectedPbdDamping=68, timeCorrectedDrag=72, lockedRightTransform=80,
+                  lockedRightTransform3d=96, tickId=144)
+    for k, off in expect.items():
+        assert getattr(S, k).offset == off, k
+        assert getattr(ob.Settings, k).offset == off, k
+
+
+@pytest.mark.parametrize("wonk,pattern", [(0.0, 0), (0.35, 0), (0.2, 1)])
+def test_product_meshgen_matches_oracle_and_reference(wonk, pattern):
+    nodes, idx, hint = xf.GenerateTetBlock(5, 3, wonkiness=wonk, pattern=pattern)
+    n2, i2 = ob.generate_tet_block(5, 3, wonkiness=wonk, pattern=pattern)
+    assert np.array_equal(nodes, n2) and np.array_equal(idx, i2)
+    if ob.have_ref():
+        r = ob.RefScene.block(5, 3, wonkiness=wonk, pattern=pattern)
+        rn, ri = r.get_mesh()
+        assert np.array_equal(nodes, rn) and np.array_equal(idx, ri)
+
+
+@pytest.mark.parametrize("wonk,pattern,density", [(0.0, 0, 1.0), (0.3, 0, 1.0), (0.3, 1, 2.5)])
+def test_host_init_bit_identical(wonk, pattern, density):
+    nodes, idx, hint = xf.GenerateTetBlock(4, 3, wonkiness=wonk, pattern=pattern)
+    g = host_scene(nodes, idx, density=density)
+    chk = ob.RefScene.mesh(nodes, idx, density=density) if ob.have_ref() else ob.OracleScene(nodes, idx, density)
+    eg, ec = g.get_elements(), chk.get_elements()
+    for k in ec:
+        assert np.array_equal(eg[k], ec[k]), k
+    Xg, Vg, wg = g.get_state()
+    Xc, Vc, wc = chk.get_state()
+    assert np.array_equal(Xg, Xc) and np.array_equal(wg, wc) and not Vg.any()
+    assert np.array_equal(g.get_rest()[2], chk.get_rest()[2])
+
+
+def test_host_init_armadillo_autoresize():
+    if not ob.have_ref():
+        pytest.skip("needs the reference's embedded Armadillo tables")
+    r = ob.RefScene.armadillo()
+    nodes, idx = r.get_mesh()
+    g = host_scene(nodes, idx, density=2.0, auto_resize=True)
+    eg, er = g.get_elements(), r.get_elements()
+    for k in er:
+        assert np.array_equal(eg[k], er[k]), k
+    assert np.array_equal(g.get_state()[0], r.get_state()[0])
+    assert np.array_equal(g.get_state()[2], r.get_state()[2])
+
+
+def check_coloring(idx_stream, colors, order, n_colors):
+    tets = idx_stream.reshape(-1, 5)[:, 1:]
+    assert colors.max() + 1 == n_colors
+    for c in range(n_colors):
+        verts = tets[colors == c].reshape(-1)
+        assert len(np.unique(verts)) == len(verts), "colour %d has two elements sharing a vertex" % c
+    # order = colour-major, stream-index-minor, a permutation
+    assert np.array_equal(np.sort(order), np.arange(len(tets)))
+    key = colors[order].astype(np.int64) * len(tets) + order
+    assert np.all(np.diff(key) > 0)
+
+
+@pytest.mark.parametrize("dims,pattern", [((8, 2), 0), ((8, 8), 0), ((7, 5), 1)])
+def test_generic_coloring_is_conflict_free(dims, pattern):
+    nodes, idx, hint = xf.GenerateTetBlock(*dims, pattern=pattern, wonkiness=0.1)
+    g = host_scene(nodes, idx)
+    check_coloring(idx, g.get_colors(), g.get_order(), g.nColors)
+    assert g.nColors <= (32 if pattern == 0 else 52)
+
+
+def test_lattice_hint_gives_24_balanced_colors():
+    nodes, idx, hint = xf.GenerateTetBlock(8, 8)
+    g = host_scene(nodes, idx, color_hint=hint)
+    assert g.nColors == 24
+    check_coloring(idx, g.get_colors(), g.get_order(), 24)
+    info = g.info()
+    assert info["minColorSize"] == info["maxColorSize"] == 8 * 8 * 8 * 6 // 24
+
+
+def test_bad_color_hint_is_rejected():
+    nodes, idx, hint = xf.GenerateTetBlock(3, 3)
+    bad = hint.copy()
+    bad[:] = 0
+    with pytest.raises(xf.XfError) as e:
+        host_scene(nodes, idx, color_hint=bad)
+    assert e.value.status == xf.XF_ERR_COLORING
+
+
+def test_armadillo_coloring():
+    if not ob.have_ref():
+        pytest.skip("needs the reference's embedded Armadillo tables")
+    r = ob.RefScene.armadillo()
+    nodes, idx = r.get_mesh()
+    g = host_scene(nodes, idx, density=2.0, auto_resize=True)
+    check_coloring(idx, g.get_colors(), g.get_order(), g.nColors)
+
+
+def test_malformed_streams_are_rejected():
+    nodes, idx, _ = xf.GenerateTetBlock(2, 2)
+    with pytest.raises(xf.XfError) as e:
+        host_scene(nodes, idx[:-1])
+    assert e.value.status == xf.XF_ERR_INVALID
+    hexrec = idx.copy()
+    hexrec[0] = 8  # CON_HEX record: not on the tet path
+    with pytest.raises(xf.XfError) as e:
+        host_scene(nodes, hexrec)
+    assert e.value.status == xf.XF_ERR_UNSUPPORTED
+    with pytest.raises(xf.XfError) as e:
+        host_scene(nodes[:-3], idx)
+    assert e.value.status == xf.XF_ERR_INVALID
+
+
+def test_no_cpu_compute_path():
+    """A host-only scene must refuse to step: the product has no CPU fallback."""
+    nodes, idx, _ = xf.GenerateTetBlock(2, 2)
+    g = host_scene(nodes, idx)
+    with pytest.raises(xf.XfError) as e:
+        g.Substep(xf.make_settings(), 1.0 / 3000.0, 1)
+    assert e.value.status == xf.XF_ERR_CUDA
+    with pytest.raises(xf.XfError):
+        g.CalculateVolume()
+
+
+def test_product_does_not_reference_the_oracle():
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "xpbd-fem_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cpp", ".cu", ".cuh", ".h", "Makefile")):
+            text = open(path, errors="ignore").read()
+            assert "xpbd_oracle" not in text and "oracle/" not in text.replace("the oracle", ""), path

@@ -1,0 +1,319 @@
+"""Host-side mirror of the reference's ``Geo`` interface over the C ABI (include/xpbd_fem_b200.h).
+
+This module is a thin ctypes binding: it owns no algorithm.  All compute happens in
+``libxpbd_fem_b200.so`` (hand-written sm_100a kernels); if the library or a CUDA device is missing the
+calls raise — there is no CPU fallback.
+
+Method names follow the reference (``Geo.h:15-35``): ``Substep``, ``Transform``, ``CalculateVolume``,
+``VertCount``, ``ElementCount``; the public members ``X, V, w, X0, O, flags, tOrder`` become getters.
+
+The directory name ``xpbd-fem_b200`` is not a valid Python identifier; load it with
+``importlib`` (see ``__graft_entry__.load_package``) under the module name ``xpbd_fem_b200``.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libxpbd_fem_b200.so")
+
+XF_ABI_VERSION = 1
+XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
+PRECISION_EXACT, PRECISION_FAST = 0, 1
+SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT = 0, 1, 2
+
+# flag word (Settings.h:9-75)
+Settings_EnergyBit = 6
+Settings_XpbdSolveBit = 11
+Settings_RayleighTypeBit = 20
+Settings_LockLeft = 1 << 26
+Settings_LockRight = 1 << 27
+Element_T4 = 5
+Energy_Mixed, Energy_MixedSel, Energy_YeohSkin, Energy_YeohSkinFast = 3, 4, 5, 7
+Pattern_Uniform, Pattern_Mirrored = 0, 1
+Rayleigh_Paper, Rayleigh_Limit, Rayleigh_Post, Rayleigh_PostAmortized = 0, 1, 2, 3
+
+
+class XfError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("xf error %d: %s" % (status, message))
+        self.status = status
+
+
+class Settings(C.Structure):
+    """xf_settings == the reference's Settings POD (Settings.h:79-102), 160 bytes."""
+    _fields_ = [
+        ("timeScale", C.c_float), ("substepsPerSecond", C.c_float), ("volumePasses", C.c_uint32), ("_pad0", C.c_uint32),
+        ("gravity", C.c_float * 2), ("compliance", C.c_float), ("damping", C.c_float), ("pbdDamping", C.c_float),
+        ("drag", C.c_float), ("poissonsRatio", C.c_float), ("wonkiness", C.c_float), ("leftRightSeparation", C.c_float),
+        ("flags", C.c_uint32),
+        ("areaAndTimeCorrectedPbdDamping", C.c_float), ("volumeAndTimeCorrectedPbdDamping", C.c_float),
+        ("amortizedAreaAndTimeCorrectedPbdDamping", C.c_float), ("amortizedVolumeAndTimeCorrectedPbdDamping", C.c_float),
+        ("timeCorrectedDrag", C.c_float), ("_pad1", C.c_uint32),
+        ("lockedRightTransform", C.c_float * 4), ("lockedRightTransform3d", C.c_float * 12),
+        ("tickId", C.c_uint32), ("_pad2", C.c_uint32 * 3),
+    ]
+
+
+class Manipulator(C.Structure):
+    _fields_ = [
+        ("pos", C.c_float * 3), ("manipPlaneNormal", C.c_float * 3), ("pick0", C.c_float * 3), ("pickDir", C.c_float * 3),
+        ("pickDirOld", C.c_float * 3), ("pickDirTarget", C.c_float * 3), ("picked", C.c_int32), ("pickedPointIdx", C.c_uint32),
+    ]
+
+
+class CreateParams(C.Structure):
+    _fields_ = [
+        ("abiVersion", C.c_uint32), ("device", C.c_int32), ("density", C.c_float), ("autoResize", C.c_int32),
+        ("precision", C.c_int32), ("schedule", C.c_int32), ("stream", C.c_void_p), ("colorHint", C.c_void_p),
+        ("colorHintCount", C.c_uint32), ("_reserved", C.c_uint32 * 5),
+    ]
+
+
+class Info(C.Structure):
+    _fields_ = [
+        ("vertCount", C.c_uint32), ("elementCount", C.c_uint32), ("colorCount", C.c_uint32), ("minColorSize", C.c_uint32),
+        ("maxColorSize", C.c_uint32), ("smCount", C.c_uint32), ("gridBlocks", C.c_uint32), ("blockThreads", C.c_uint32),
+        ("elementRecordBytes", C.c_uint32), ("schedule", C.c_uint32), ("kernelLaunches", C.c_uint64), ("l2Bytes", C.c_uint64),
+    ]
+
+
+def make_settings(energy=Energy_MixedSel, simultaneous=True, poisson=0.5, compliance=1.0, gravity=(0.0, -0.4905), damping=0.0,
+                  rayleigh=Rayleigh_Post, lock_left=True, lock_right=False, drag_tc=0.0, volume_passes=0, pbd_damping=0.0,
+                  substeps_per_second=3000.0):
+    """A Settings block with the web demo's defaults (wasm/ui.js:69-91) unless overridden."""
+    s = Settings()
+    s.timeScale = 1.0
+    s.substepsPerSecond = substeps_per_second
+    s.volumePasses = volume_passes
+    s.gravity[0], s.gravity[1] = gravity
+    s.compliance = compliance
+    s.damping = damping
+    s.pbdDamping = pbd_damping
+    s.poissonsRatio = poisson
+    s.leftRightSeparation = 1.0
+    s.flags = (Element_T4 | (energy << Settings_EnergyBit) | ((1 if simultaneous else 0) << Settings_XpbdSolveBit)
+               | (rayleigh << Settings_RayleighTypeBit) | (Settings_LockLeft if lock_left else 0)
+               | (Settings_LockRight if lock_right else 0))
+    s.timeCorrectedDrag = drag_tc
+    s.lockedRightTransform[0] = s.lockedRightTransform[3] = 1.0
+    s.lockedRightTransform3d[0] = s.lockedRightTransform3d[5] = s.lockedRightTransform3d[10] = 1.0
+    return s
+
+
+_lib = None
+
+EXPORTS = [
+    "xf_last_error", "xf_device_count", "xf_default_create_params", "xf_generate_tet_block", "xf_create", "xf_destroy",
+    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_elements", "xf_substep",
+    "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
+    "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
+]
+
+
+def lib():
+    """Load libxpbd_fem_b200.so (fails loudly if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OSError("%s is missing: run `make -C xpbd-fem_b200` (or __graft_entry__.build())" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, u32, f32, i32 = C.c_void_p, C.c_uint32, C.c_float, C.c_int
+    L.xf_last_error.restype = C.c_char_p
+    L.xf_device_count.argtypes = [C.POINTER(C.c_int)]
+    L.xf_default_create_params.argtypes = [C.POINTER(CreateParams)]
+    L.xf_default_create_params.restype = None
+    L.xf_generate_tet_block.argtypes = [u32, u32, u32, f32, f32, f32, u32, f32, vp, vp, vp]
+    L.xf_create.argtypes = [C.POINTER(CreateParams), vp, u32, vp, u32, C.POINTER(vp)]
+    L.xf_destroy.argtypes = [vp]
+    for n in ("xf_vert_count", "xf_element_count", "xf_color_count"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = u32
+    L.xf_get_order.argtypes = [vp, vp]
+    L.xf_get_colors.argtypes = [vp, vp]
+    L.xf_get_elements.argtypes = [vp] * 7
+    L.xf_substep.argtypes = [vp, vp, vp, f32, u32]
+    L.xf_sync.argtypes = [vp]
+    L.xf_set_ground.argtypes = [vp, i32, f32, f32]
+    L.xf_set_handles.argtypes = [vp, u32, vp, vp]
+    L.xf_get_state.argtypes = [vp, vp, vp, vp]
+    L.xf_set_state.argtypes = [vp, vp, vp, vp]
+    L.xf_get_rest.argtypes = [vp, vp, vp, vp]
+    L.xf_get_origin.argtypes = [vp, vp]
+    L.xf_get_state_async.argtypes = [vp, vp, vp]
+    L.xf_set_state_async.argtypes = [vp, vp, vp]
+    L.xf_transform.argtypes = [vp, vp]
+    L.xf_volume.argtypes = [vp, C.POINTER(f32)]
+    L.xf_stats.argtypes = [vp, vp, vp]
+    L.xf_get_info.argtypes = [vp, C.POINTER(Info)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise XfError(rc, lib().xf_last_error().decode("utf-8", "replace"))
+
+
+def _vp(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = lib().xf_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def block_scale(dim=3.0):
+    """(0.7f * kSpacing) * dim in fp32, as Demo::UpdateSettings scales its blocks (Demo.cpp:16, 318)."""
+    k_spacing = np.float32(np.float32(20.0) / np.float32(100.0)) / np.float32(31.0)
+    return float(np.float32(np.float32(0.7) * k_spacing) * np.float32(dim))
+
+
+def GenerateTetBlock(width, height, depth=None, scale=None, pattern=Pattern_Uniform, wonkiness=0.0):
+    """MeshGen.cpp:223-244 on the host.  Returns (nodes f32[3*nV], idxStream u32[30*nHex], colorHint u32[6*nHex])."""
+    depth = height if depth is None else depth
+    if scale is None:
+        scale = (block_scale(),) * 3
+    nodes = np.empty(3 * (width + 1) * (height + 1) * (depth + 1), dtype=np.float32)
+    idx = np.empty(30 * width * height * depth, dtype=np.uint32)
+    hint = np.empty(6 * width * height * depth, dtype=np.uint32)
+    _check(lib().xf_generate_tet_block(width, height, depth, scale[0], scale[1], scale[2], pattern, wonkiness, _vp(nodes), _vp(idx),
+                                       _vp(hint)))
+    return nodes, idx, hint
+
+
+class GeoLinear3dCuda:
+    """One tet mesh resident on a B200; the drop-in for the reference's GeoLinear3d on the Substep path."""
+
+    def __init__(self, nodes, idx_stream, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
+                 schedule=SCHEDULE_AUTO, color_hint=None, stream=None):
+        L = lib()
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        p = CreateParams()
+        L.xf_default_create_params(C.byref(p))
+        p.device = device
+        p.density = density
+        p.autoResize = 1 if auto_resize else 0
+        p.precision = precision
+        p.schedule = schedule
+        p.stream = stream
+        if color_hint is not None:
+            color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)
+            p.colorHint = color_hint.ctypes.data
+            p.colorHintCount = color_hint.size
+        h = C.c_void_p()
+        self._h = None
+        _check(L.xf_create(C.byref(p), _vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, C.byref(h)))
+        self._h = h
+        self.nV = L.xf_vert_count(h)
+        self.nT = L.xf_element_count(h)
+        self.nColors = L.xf_color_count(h)
+
+    def close(self):
+        if self._h:
+            lib().xf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- Geo interface -------------------------------------------------------------------------
+    def VertCount(self):
+        return self.nV
+
+    def ElementCount(self):
+        return self.nT
+
+    def Substep(self, settings, dt, n=1, manip=None):
+        """Geo::Substep(settings, manip, dt), n times (asynchronous)."""
+        _check(lib().xf_substep(self._h, C.byref(settings), C.byref(manip) if manip is not None else None, float(dt), int(n)))
+
+    def Sync(self):
+        _check(lib().xf_sync(self._h))
+
+    def Transform(self, m9):
+        m9 = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)
+        _check(lib().xf_transform(self._h, _vp(m9)))
+
+    def CalculateVolume(self):
+        v = C.c_float()
+        _check(lib().xf_volume(self._h, C.byref(v)))
+        return float(v.value)
+
+    # ---- public members of the reference's Geo3d / GeoLinear3d ------------------------------------
+    def get_order(self):
+        o = np.empty(self.nT, dtype=np.uint32)
+        _check(lib().xf_get_order(self._h, _vp(o)))
+        return o
+
+    def get_colors(self):
+        c = np.empty(self.nT, dtype=np.uint32)
+        _check(lib().xf_get_colors(self._h, _vp(c)))
+        return c
+
+    def get_state(self):
+        X = np.empty((self.nV, 3), dtype=np.float64)
+        V = np.empty((self.nV, 3), dtype=np.float64)
+        w = np.empty(self.nV, dtype=np.float32)
+        _check(lib().xf_get_state(self._h, _vp(X), _vp(V), _vp(w)))
+        return X, V, w
+
+    def set_state(self, X=None, V=None, w=None):
+        X = None if X is None else np.ascontiguousarray(X, dtype=np.float64)
+        V = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+        w = None if w is None else np.ascontiguousarray(w, dtype=np.float32)
+        _check(lib().xf_set_state(self._h, _vp(X), _vp(V), _vp(w)))
+
+    def get_rest(self):
+        X0 = np.empty((self.nV, 3), dtype=np.float64)
+        O = np.empty((self.nV, 3), dtype=np.float64)
+        flags = np.empty(self.nV, dtype=np.uint8)
+        _check(lib().xf_get_rest(self._h, _vp(X0), _vp(O), _vp(flags)))
+        return X0, O, flags
+
+    def get_origin(self):
+        o = np.empty(3, dtype=np.float32)
+        _check(lib().xf_get_origin(self._h, _vp(o)))
+        return o
+
+    def get_elements(self):
+        n = self.nT
+        out = dict(idx=np.empty((n, 4), np.uint32), Qi=np.empty((n, 9), np.float32), QQ=np.empty((n, 3), np.float32),
+                   QR=np.empty((n, 3), np.float32), volume=np.empty(n, np.float32), area=np.empty(n, np.float32))
+        _check(lib().xf_get_elements(self._h, _vp(out["idx"]), _vp(out["Qi"]), _vp(out["QQ"]), _vp(out["QR"]), _vp(out["volume"]),
+                                     _vp(out["area"])))
+        return out
+
+    # ---- extensions / helpers ---------------------------------------------------------------------
+    def set_ground(self, enabled, y0=0.0, friction=0.0):
+        _check(lib().xf_set_ground(self._h, 1 if enabled else 0, y0, friction))
+
+    def set_handles(self, vert_idx, targets):
+        vert_idx = np.ascontiguousarray(vert_idx, dtype=np.uint32)
+        targets = np.ascontiguousarray(targets, dtype=np.float32).reshape(-1)
+        _check(lib().xf_set_handles(self._h, vert_idx.size, _vp(vert_idx), _vp(targets)))
+
+    def stats(self, settings):
+        out = np.zeros(6, dtype=np.float64)
+        _check(lib().xf_stats(self._h, C.byref(settings), _vp(out)))
+        return dict(volume=out[0], kinetic=out[1], gravitational=out[2], deviatoric=out[3], volumetric=out[4], nonfinite=out[5])
+
+    def info(self):
+        i = Info()
+        _check(lib().xf_get_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in Info._fields_}
+
+    def get_state_async(self, X_ptr, V_ptr):
+        """Enqueue device->host copies into caller-owned (pinned) buffers; pointers are integers or None."""
+        _check(lib().xf_get_state_async(self._h, X_ptr, V_ptr))
+
+    def set_state_async(self, X_ptr, V_ptr):
+        _check(lib().xf_set_state_async(self._h, X_ptr, V_ptr))

@@ -1,0 +1,450 @@
+// C ABI of libxpbd_fem_b200.so (include/xpbd_fem_b200.h): scene lifetime, uploads, stepping, state access.
+// Host C++ only; every device operation goes through the launchers in xf_kernels.cu.
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+
+#include "xf_scene.h"
+
+using namespace xf;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int Fail(int status, const std::string& msg) {
+	g_lastError = msg;
+	return status;
+}
+int FailCuda(cudaError_t e, const char* what) {
+	g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
+	return XF_ERR_CUDA;
+}
+#define XF_CUDA(call)                                                \
+	do {                                                             \
+		cudaError_t _e = (call);                                     \
+		if (_e != cudaSuccess) { return FailCuda(_e, #call); }       \
+	} while (0)
+
+template <typename T>
+cudaError_t Upload(T** dst, const std::vector<T>& src) {
+	cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * std::max<size_t>(src.size(), 1));
+	if (e != cudaSuccess) { return e; }
+	return cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+struct xf_scene {
+	HostMesh mesh;
+	DeviceScene dev;
+	int device = -1;          // < 0: host-only scene (introspection of init/colouring; cannot step)
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	int precision = XF_PRECISION_EXACT;
+	int schedule = XF_SCHEDULE_AUTO;
+	bool cooperative = false;
+	std::map<uint32_t, LaunchShape> shapes; // per energy
+	int smCount = 0;
+	size_t l2Bytes = 0;
+	uint64_t launches = 0;
+	// extensions
+	uint32_t groundOn = 0;
+	float groundY = 0.0f, groundFriction = 0.0f;
+	uint32_t handleCount = 0;
+	uint32_t handleIdx[kMaxHandles];
+	float handleTarget[kMaxHandles][3];
+	// staging for packed state transfers
+	double* dPackX = nullptr;
+	double* dPackV = nullptr;
+	float* dPackW = nullptr;
+	std::vector<float> hostScratch;
+};
+
+namespace {
+
+void FreeDevice(xf_scene* s) {
+	if (s->device < 0) { return; }
+	cudaSetDevice(s->device);
+	DeviceScene& d = s->dev;
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, d.eArea, d.eScratch, d.statScratch, d.streamToSorted,
+		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
+	for (void* p : ptrs) { if (p) { cudaFree(p); } }
+	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
+}
+
+int UploadScene(xf_scene* s) {
+	const HostMesh& m = s->mesh;
+	DeviceScene& d = s->dev;
+	d.nV = m.nV;
+	d.nT = m.nT;
+	d.nColors = (uint32_t)m.colorStart.size() - 1;
+	std::vector<VertexRec> xw(m.nV);
+	std::vector<double4> x0(m.nV), zero(m.nV, double4{ 0.0, 0.0, 0.0, 0.0 });
+	for (uint32_t i = 0; i < m.nV; i++) {
+		xw[i] = VertexRec{ m.X0[3 * (size_t)i], m.X0[3 * (size_t)i + 1], m.X0[3 * (size_t)i + 2], m.w[i], (uint32_t)m.flags[i] };
+		x0[i] = double4{ xw[i].x, xw[i].y, xw[i].z, 0.0 };
+	}
+	XF_CUDA(Upload(&d.Xw, xw));
+	XF_CUDA(Upload(&d.O, x0));
+	XF_CUDA(Upload(&d.X0, x0));
+	XF_CUDA(Upload(&d.V, zero));
+	// colour-sorted element planes
+	std::vector<uint4> eIdx(m.nT);
+	std::vector<float4> q0(m.nT), q1(m.nT), c0(m.nT);
+	std::vector<float2> q2(m.nT), c1(m.nT);
+	std::vector<float> area(m.nT);
+	std::vector<uint32_t> streamToSorted(m.nT);
+	for (uint32_t pos = 0; pos < m.nT; pos++) {
+		const uint32_t e = m.order[pos];
+		streamToSorted[e] = pos;
+		const uint32_t* v = &m.idx[4 * (size_t)e];
+		const float* Q = &m.Qi[9 * (size_t)e];
+		eIdx[pos] = uint4{ v[0], v[1], v[2], v[3] };
+		q0[pos] = float4{ Q[0], Q[1], Q[2], Q[3] };
+		q1[pos] = float4{ Q[4], Q[5], Q[6], Q[7] };
+		q2[pos] = float2{ Q[8], m.volume[e] };
+		c0[pos] = float4{ m.QQ[3 * (size_t)e], m.QQ[3 * (size_t)e + 1], m.QQ[3 * (size_t)e + 2], m.QR[3 * (size_t)e] };
+		c1[pos] = float2{ m.QR[3 * (size_t)e + 1], m.QR[3 * (size_t)e + 2] };
+		area[pos] = m.area[e];
+	}
+	XF_CUDA(Upload(&d.eIdx, eIdx));
+	XF_CUDA(Upload(&d.eQ0, q0));
+	XF_CUDA(Upload(&d.eQ1, q1));
+	XF_CUDA(Upload(&d.eQ2, q2));
+	XF_CUDA(Upload(&d.eC0, c0));
+	XF_CUDA(Upload(&d.eC1, c1));
+	XF_CUDA(Upload(&d.eArea, area));
+	XF_CUDA(Upload(&d.streamToSorted, streamToSorted));
+	XF_CUDA(cudaMalloc((void**)&d.eScratch, sizeof(float) * m.nT));
+	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
+	XF_CUDA(cudaMalloc((void**)&d.barrier, sizeof(unsigned int) * 32));
+	XF_CUDA(cudaMemset(d.barrier, 0, sizeof(unsigned int) * 32));
+	XF_CUDA(cudaMalloc((void**)&s->dPackX, sizeof(double) * 3 * m.nV));
+	XF_CUDA(cudaMalloc((void**)&s->dPackV, sizeof(double) * 3 * m.nV));
+	XF_CUDA(cudaMalloc((void**)&s->dPackW, sizeof(float) * m.nV));
+	return XF_OK;
+}
+
+int NeedDevice(const xf_scene* s) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	if (s->device < 0) { return Fail(XF_ERR_CUDA, "scene was created host-only (device < 0): there is no CPU compute path"); }
+	cudaError_t e = cudaSetDevice(s->device);
+	if (e != cudaSuccess) { return FailCuda(e, "cudaSetDevice"); }
+	return XF_OK;
+}
+
+int BuildParams(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, float dt, SubstepParams* p) {
+	std::string err;
+	int rc = FillSubstepParams(st, manip, dt, s->mesh, p, &err);
+	if (rc != XF_OK) { return Fail(rc, err); }
+	p->groundOn = s->groundOn;
+	p->groundY = s->groundY;
+	p->groundKeep = 1.0f - s->groundFriction;
+	p->handleCount = s->handleCount;
+	memcpy(p->handleIdx, s->handleIdx, sizeof(p->handleIdx));
+	memcpy(p->handleTarget, s->handleTarget, sizeof(p->handleTarget));
+	return XF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* xf_last_error(void) { return g_lastError.c_str(); }
+
+int xf_device_count(int* outCount) {
+	if (!outCount) { return Fail(XF_ERR_INVALID, "null outCount"); }
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess) { *outCount = 0; return FailCuda(e, "cudaGetDeviceCount"); }
+	*outCount = n;
+	return XF_OK;
+}
+
+void xf_default_create_params(xf_create_params* p) {
+	if (!p) { return; }
+	memset(p, 0, sizeof(*p));
+	p->abiVersion = XF_ABI_VERSION;
+	p->device = 0;
+	p->density = 1.0f;
+	p->autoResize = 0;
+	p->precision = XF_PRECISION_EXACT;
+	p->schedule = XF_SCHEDULE_AUTO;
+}
+
+int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount,
+              xf_scene** outScene) {
+	if (!params || !outScene) { return Fail(XF_ERR_INVALID, "null params/outScene"); }
+	*outScene = nullptr;
+	if (params->abiVersion != XF_ABI_VERSION) { return Fail(XF_ERR_INVALID, "xf_create_params.abiVersion mismatch"); }
+	if (params->precision != XF_PRECISION_EXACT && params->precision != XF_PRECISION_FAST) { return Fail(XF_ERR_INVALID, "bad precision"); }
+	if (params->schedule < XF_SCHEDULE_AUTO || params->schedule > XF_SCHEDULE_PERSISTENT) { return Fail(XF_ERR_INVALID, "bad schedule"); }
+	xf_scene* s = new (std::nothrow) xf_scene();
+	if (!s) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
+	std::string err;
+	int rc = PrepareMesh(nodeXYZ, nodeFloatCount, idxStream, idxCount, params->density, params->autoResize != 0, params->colorHint,
+	                     params->colorHintCount, &s->mesh, &err);
+	if (rc != XF_OK) { delete s; return Fail(rc, err); }
+	s->precision = params->precision;
+	s->schedule = params->schedule;
+	s->device = params->device;
+	if (s->device >= 0) {
+		cudaError_t e = cudaSetDevice(s->device);
+		if (e != cudaSuccess) { delete s; return FailCuda(e, "cudaSetDevice"); }
+		cudaDeviceProp prop;
+		e = cudaGetDeviceProperties(&prop, s->device);
+		if (e != cudaSuccess) { delete s; return FailCuda(e, "cudaGetDeviceProperties"); }
+		s->smCount = prop.multiProcessorCount;
+		s->l2Bytes = (size_t)prop.l2CacheSize;
+		s->cooperative = prop.cooperativeLaunch != 0;
+		if (params->stream) {
+			s->stream = (cudaStream_t)params->stream;
+		} else {
+			e = cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking);
+			if (e != cudaSuccess) { delete s; return FailCuda(e, "cudaStreamCreate"); }
+			s->ownStream = true;
+		}
+		rc = UploadScene(s);
+		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
+		if (s->schedule == XF_SCHEDULE_AUTO) { s->schedule = s->cooperative ? XF_SCHEDULE_PERSISTENT : XF_SCHEDULE_LAUNCH_PER_COLOR; }
+		if (s->schedule == XF_SCHEDULE_PERSISTENT && !s->cooperative) {
+			FreeDevice(s); delete s;
+			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT)");
+		}
+	}
+	*outScene = s;
+	return XF_OK;
+}
+
+int xf_destroy(xf_scene* s) {
+	if (!s) { return XF_OK; }
+	if (s->device >= 0) { cudaSetDevice(s->device); if (s->stream) { cudaStreamSynchronize(s->stream); } }
+	FreeDevice(s);
+	delete s;
+	return XF_OK;
+}
+
+uint32_t xf_vert_count(const xf_scene* s) { return s ? s->mesh.nV : 0; }
+uint32_t xf_element_count(const xf_scene* s) { return s ? s->mesh.nT : 0; }
+uint32_t xf_color_count(const xf_scene* s) { return s ? (uint32_t)s->mesh.colorStart.size() - 1 : 0; }
+
+int xf_get_order(const xf_scene* s, uint32_t* order) {
+	if (!s || !order) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(order, s->mesh.order.data(), sizeof(uint32_t) * s->mesh.nT);
+	return XF_OK;
+}
+int xf_get_colors(const xf_scene* s, uint32_t* colorOfElement) {
+	if (!s || !colorOfElement) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(colorOfElement, s->mesh.color.data(), sizeof(uint32_t) * s->mesh.nT);
+	return XF_OK;
+}
+int xf_get_elements(const xf_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	const HostMesh& m = s->mesh;
+	if (idx4) { memcpy(idx4, m.idx.data(), sizeof(uint32_t) * m.idx.size()); }
+	if (Qi9) { memcpy(Qi9, m.Qi.data(), sizeof(float) * m.Qi.size()); }
+	if (QQ3) { memcpy(QQ3, m.QQ.data(), sizeof(float) * m.QQ.size()); }
+	if (QR3) { memcpy(QR3, m.QR.data(), sizeof(float) * m.QR.size()); }
+	if (volume) { memcpy(volume, m.volume.data(), sizeof(float) * m.volume.size()); }
+	if (surfaceArea) { memcpy(surfaceArea, m.area.data(), sizeof(float) * m.area.size()); }
+	return XF_OK;
+}
+
+int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, float dt, uint32_t n) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!st) { return Fail(XF_ERR_INVALID, "null settings"); }
+	if (n == 0) { return XF_OK; }
+	SubstepParams p;
+	rc = BuildParams(s, st, manip, dt, &p);
+	if (rc != XF_OK) { return rc; }
+	const bool exact = s->precision == XF_PRECISION_EXACT;
+	if (s->schedule == XF_SCHEDULE_PERSISTENT) {
+		auto it = s->shapes.find(p.energy);
+		if (it == s->shapes.end()) {
+			LaunchShape shape;
+			XF_CUDA(QueryLaunchShape(s->device, p.energy, exact, &shape));
+			it = s->shapes.emplace(p.energy, shape).first;
+		}
+		XF_CUDA(LaunchSubstepsPersistent(s->dev, p, exact, n, it->second, s->stream, &s->launches));
+	} else {
+		XF_CUDA(LaunchSubstepsPerColor(s->dev, p, exact, n, s->stream, &s->launches));
+	}
+	return XF_OK;
+}
+
+int xf_sync(xf_scene* s) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	XF_CUDA(cudaStreamSynchronize(s->stream));
+	return XF_OK;
+}
+
+int xf_set_ground(xf_scene* s, int enabled, float y0, float friction) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	s->groundOn = enabled ? 1u : 0u;
+	s->groundY = y0;
+	s->groundFriction = friction;
+	return XF_OK;
+}
+
+int xf_set_handles(xf_scene* s, uint32_t count, const uint32_t* vertIdx, const float* targetXYZ) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	if (count > (uint32_t)kMaxHandles) { return Fail(XF_ERR_INVALID, "at most 64 drag handles"); }
+	if (count && (!vertIdx || !targetXYZ)) { return Fail(XF_ERR_INVALID, "null handle arrays"); }
+	for (uint32_t k = 0; k < count; k++) {
+		if (vertIdx[k] >= s->mesh.nV) { return Fail(XF_ERR_INVALID, "handle vertex index out of range"); }
+	}
+	s->handleCount = count;
+	for (uint32_t k = 0; k < count; k++) {
+		s->handleIdx[k] = vertIdx[k];
+		for (int j = 0; j < 3; j++) { s->handleTarget[k][j] = targetXYZ[3 * (size_t)k + j]; }
+	}
+	return XF_OK;
+}
+
+int xf_get_state_async(xf_scene* s, double* X, double* V) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	XF_CUDA(LaunchPackState(s->dev, X ? s->dPackX : nullptr, V ? s->dPackV : nullptr, nullptr, s->stream, &s->launches));
+	const size_t bytes = sizeof(double) * 3 * s->mesh.nV;
+	if (X) { XF_CUDA(cudaMemcpyAsync(X, s->dPackX, bytes, cudaMemcpyDeviceToHost, s->stream)); }
+	if (V) { XF_CUDA(cudaMemcpyAsync(V, s->dPackV, bytes, cudaMemcpyDeviceToHost, s->stream)); }
+	return XF_OK;
+}
+
+int xf_set_state_async(xf_scene* s, const double* X, const double* V) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	const size_t bytes = sizeof(double) * 3 * s->mesh.nV;
+	if (X) { XF_CUDA(cudaMemcpyAsync(s->dPackX, X, bytes, cudaMemcpyHostToDevice, s->stream)); }
+	if (V) { XF_CUDA(cudaMemcpyAsync(s->dPackV, V, bytes, cudaMemcpyHostToDevice, s->stream)); }
+	XF_CUDA(LaunchUnpackState(s->dev, X ? s->dPackX : nullptr, V ? s->dPackV : nullptr, nullptr, s->stream, &s->launches));
+	return XF_OK;
+}
+
+int xf_get_state(xf_scene* s, double* X, double* V, float* w) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	if (s->device < 0) { // host-only scene: the initial state
+		const HostMesh& m = s->mesh;
+		if (X) { memcpy(X, m.X0.data(), sizeof(double) * 3 * m.nV); }
+		if (V) { memset(V, 0, sizeof(double) * 3 * m.nV); }
+		if (w) { memcpy(w, m.w.data(), sizeof(float) * m.nV); }
+		return XF_OK;
+	}
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	XF_CUDA(LaunchPackState(s->dev, X ? s->dPackX : nullptr, V ? s->dPackV : nullptr, w ? s->dPackW : nullptr, s->stream, &s->launches));
+	const size_t bytes = sizeof(double) * 3 * s->mesh.nV;
+	if (X) { XF_CUDA(cudaMemcpyAsync(X, s->dPackX, bytes, cudaMemcpyDeviceToHost, s->stream)); }
+	if (V) { XF_CUDA(cudaMemcpyAsync(V, s->dPackV, bytes, cudaMemcpyDeviceToHost, s->stream)); }
+	if (w) { XF_CUDA(cudaMemcpyAsync(w, s->dPackW, sizeof(float) * s->mesh.nV, cudaMemcpyDeviceToHost, s->stream)); }
+	XF_CUDA(cudaStreamSynchronize(s->stream));
+	return XF_OK;
+}
+
+int xf_set_state(xf_scene* s, const double* X, const double* V, const float* w) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	const size_t bytes = sizeof(double) * 3 * s->mesh.nV;
+	if (X) { XF_CUDA(cudaMemcpyAsync(s->dPackX, X, bytes, cudaMemcpyHostToDevice, s->stream)); }
+	if (V) { XF_CUDA(cudaMemcpyAsync(s->dPackV, V, bytes, cudaMemcpyHostToDevice, s->stream)); }
+	if (w) { XF_CUDA(cudaMemcpyAsync(s->dPackW, w, sizeof(float) * s->mesh.nV, cudaMemcpyHostToDevice, s->stream)); }
+	XF_CUDA(LaunchUnpackState(s->dev, X ? s->dPackX : nullptr, V ? s->dPackV : nullptr, w ? s->dPackW : nullptr, s->stream, &s->launches));
+	XF_CUDA(cudaStreamSynchronize(s->stream));
+	return XF_OK;
+}
+
+int xf_get_rest(xf_scene* s, double* X0, double* O, uint8_t* flags) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	const HostMesh& m = s->mesh;
+	if (X0) { memcpy(X0, m.X0.data(), sizeof(double) * 3 * m.nV); }
+	if (flags) { memcpy(flags, m.flags.data(), m.nV); }
+	if (O) {
+		if (s->device < 0) { memcpy(O, m.X0.data(), sizeof(double) * 3 * m.nV); return XF_OK; }
+		int rc = NeedDevice(s);
+		if (rc != XF_OK) { return rc; }
+		std::vector<double4> tmp(m.nV);
+		XF_CUDA(cudaStreamSynchronize(s->stream));
+		XF_CUDA(cudaMemcpy(tmp.data(), s->dev.O, sizeof(double4) * m.nV, cudaMemcpyDeviceToHost));
+		for (uint32_t i = 0; i < m.nV; i++) { O[3 * (size_t)i] = tmp[i].x; O[3 * (size_t)i + 1] = tmp[i].y; O[3 * (size_t)i + 2] = tmp[i].z; }
+	}
+	return XF_OK;
+}
+
+int xf_get_origin(const xf_scene* s, float* origin3) {
+	if (!s || !origin3) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(origin3, s->mesh.origin, sizeof(float) * 3);
+	return XF_OK;
+}
+
+int xf_transform(xf_scene* s, const float* m9) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!m9) { return Fail(XF_ERR_INVALID, "null matrix"); }
+	XF_CUDA(LaunchTransform(s->dev, m9, s->stream, &s->launches));
+	// origin = (t4 * vec4(origin, 1)).xyz, Geo.cpp:363 (fp32, left-assoc dot of each row with (x,y,z,1))
+	const float ox = s->mesh.origin[0], oy = s->mesh.origin[1], oz = s->mesh.origin[2];
+	s->mesh.origin[0] = m9[0] * ox + m9[3] * oy + 0.0f * oz + m9[6] * 1.0f;
+	s->mesh.origin[1] = m9[1] * ox + m9[4] * oy + 0.0f * oz + m9[7] * 1.0f;
+	s->mesh.origin[2] = m9[2] * ox + m9[5] * oy + 1.0f * oz + 0.0f * 1.0f;
+	return XF_OK;
+}
+
+int xf_volume(xf_scene* s, float* outVolume) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!outVolume) { return Fail(XF_ERR_INVALID, "null outVolume"); }
+	XF_CUDA(LaunchElementVolumes(s->dev, s->stream, &s->launches));
+	s->hostScratch.resize(s->mesh.nT);
+	XF_CUDA(cudaMemcpyAsync(s->hostScratch.data(), s->dev.eScratch, sizeof(float) * s->mesh.nT, cudaMemcpyDeviceToHost, s->stream));
+	XF_CUDA(cudaStreamSynchronize(s->stream));
+	float volume = 0.0f; // fp32 running sum in element order, Geo.cpp:828-829
+	for (uint32_t e = 0; e < s->mesh.nT; e++) { volume += s->hostScratch[e]; }
+	*outVolume = volume;
+	return XF_OK;
+}
+
+int xf_stats(xf_scene* s, const xf_settings* st, double* out6) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!st || !out6) { return Fail(XF_ERR_INVALID, "null argument"); }
+	SubstepParams p;
+	rc = BuildParams(s, st, nullptr, 1.0f, &p);
+	if (rc != XF_OK) { return rc; }
+	XF_CUDA(LaunchStats(s->dev, p, (double)st->gravity[0], (double)st->gravity[1], s->smCount, s->stream, &s->launches));
+	XF_CUDA(cudaMemcpyAsync(out6, s->dev.statScratch, sizeof(double) * 6, cudaMemcpyDeviceToHost, s->stream));
+	XF_CUDA(cudaStreamSynchronize(s->stream));
+	return XF_OK;
+}
+
+int xf_get_info(const xf_scene* s, xf_info* out) {
+	if (!s || !out) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memset(out, 0, sizeof(*out));
+	const HostMesh& m = s->mesh;
+	out->vertCount = m.nV;
+	out->elementCount = m.nT;
+	out->colorCount = (uint32_t)m.colorStart.size() - 1;
+	uint32_t mn = 0xffffffffu, mx = 0;
+	for (size_t c = 0; c + 1 < m.colorStart.size(); c++) {
+		uint32_t n = m.colorStart[c + 1] - m.colorStart[c];
+		mn = std::min(mn, n);
+		mx = std::max(mx, n);
+	}
+	out->minColorSize = mn;
+	out->maxColorSize = mx;
+	out->smCount = (uint32_t)s->smCount;
+	if (!s->shapes.empty()) {
+		out->gridBlocks = (uint32_t)s->shapes.begin()->second.gridBlocks;
+		out->blockThreads = (uint32_t)s->shapes.begin()->second.blockThreads;
+	}
+	out->elementRecordBytes = s->precision == XF_PRECISION_EXACT ? 80u : 56u;
+	out->schedule = (uint32_t)s->schedule;
+	out->kernelLaunches = s->launches;
+	out->l2Bytes = s->l2Bytes;
+	return XF_OK;
+}
+
+}  // extern "C"

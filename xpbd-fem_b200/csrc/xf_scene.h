@@ -1,0 +1,132 @@
+// Internal types shared by the host side (xf_api.cpp, xf_prepare.cpp) and the kernels (xf_kernels.cu).
+// Nothing here crosses the C ABI.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/xpbd_fem_b200.h"
+
+namespace xf {
+
+// ------------------------------------------------------------------------------------------------
+// HBM layout
+//
+// Vertices (AoS, one 32-byte L2 sector per vertex so an element gather costs exactly 4 sectors):
+//   VertexRec  Xw[nV]   { double x, y, z; float w; uint32 flags }   position + inverse mass + lock flags
+//   double4    O[nV], V[nV], X0[nV]                                  (.w unused)
+// Elements (SoA planes, sorted by colour then by original index, so a warp streams each plane with
+// fully coalesced 16/8-byte loads):
+//   uint4  eIdx[nT]        vertex indices
+//   float4 eQ0[nT]         Qi[0][0] Qi[0][1] Qi[0][2] Qi[1][0]     (Qi column-major like the reference's mat3)
+//   float4 eQ1[nT]         Qi[1][1] Qi[1][2] Qi[2][0] Qi[2][1]
+//   float2 eQ2[nT]         Qi[2][2] volume                          -> 56 B/element (XF_PRECISION_FAST)
+//   float4 eC0[nT]         QQ0 QQ1 QQ2 QR0                          (+24 B: the reference's own prefactored
+//   float2 eC1[nT]         QR1 QR2                                   coefficients, XF_PRECISION_EXACT only)
+//   float  eArea[nT]       surfaceArea (PbdDamp only)
+// ------------------------------------------------------------------------------------------------
+struct alignas(32) VertexRec {
+	double x, y, z;
+	float w;
+	uint32_t flags;
+};
+
+struct DeviceScene {
+	uint32_t nV = 0, nT = 0, nColors = 0;
+	VertexRec* Xw = nullptr;
+	double4* O = nullptr;
+	double4* V = nullptr;
+	double4* X0 = nullptr;
+	uint4* eIdx = nullptr;
+	float4* eQ0 = nullptr;
+	float4* eQ1 = nullptr;
+	float2* eQ2 = nullptr;
+	float4* eC0 = nullptr;
+	float2* eC1 = nullptr;
+	float* eArea = nullptr;
+	float* eScratch = nullptr;      // nT floats (per-element volume terms)
+	double* statScratch = nullptr;  // reduction outputs
+	uint32_t* streamToSorted = nullptr; // nT: position of stream element s in the colour-sorted planes
+	unsigned int* barrier = nullptr; // grid-barrier counter
+};
+
+constexpr int kMaxHandles = 64;
+constexpr int kMaxColors = 256;
+
+// Everything one xf_substep call needs, passed to the kernels by value (__grid_constant__).
+// All derived fp32 constants are computed on the host with the reference's expressions
+// (file compiled with -ffp-contract=off) so the device sees the very same bits.
+struct SubstepParams {
+	float dt, dt2, invDt;      // dt, dt*dt, 1.0f/dt
+	float gdtX, gdtY;          // gravity.x*dt, gravity.y*dt                       Geo.cpp:308
+	float keep;                // 1.0f - timeCorrectedDrag                         Geo.cpp:309
+	float invMu, invLambda, a; // 1.0f/mu, 1.0f/lambda, 1.0f + mu/lambda           Fem.cpp:445-449
+	float damping;             // settings.damping                                 Fem.cpp:450
+	float compliance;          // settings.compliance (volume passes, Fem.cpp:844)
+	float pbdDamping;          // volumeAndTimeCorrectedPbdDamping to use this call
+	float dampDamping;         // damping used by the post-solve Damp sweep (x8 when amortised, Geo.cpp:349)
+	uint32_t energy;           // XF_ENERGY_*
+	uint32_t simultaneous;     // Settings_XpbdSolveBit
+	uint32_t rayleigh;         // XF_RAYLEIGH_*
+	uint32_t lockLeft, lockRight;
+	uint32_t volumePasses;
+	uint32_t tickId;           // of the first substep of the call
+	uint32_t doDamp, doPbdDamp;
+	float lockT[12];           // lockedRightTransform3d, padded columns
+	float origin[3];
+	uint32_t groundOn;
+	float groundY, groundKeep; // y0, 1.0f - friction
+	uint32_t manipOn, manipIdx;
+	float manipTarget[3];
+	float c18;                 // 1.8f / (dt*dt)                                   Geo.cpp:338
+	uint32_t handleCount;
+	uint32_t handleIdx[kMaxHandles];
+	float handleTarget[kMaxHandles][3];
+	uint32_t colorStart[kMaxColors + 1];
+	uint32_t nColors;
+};
+
+struct LaunchShape {
+	int blockThreads = 256;
+	int gridBlocks = 0;     // persistent grid (co-resident)
+	int smCount = 0;
+};
+
+// ---- host-side prepared mesh (xf_prepare.cpp) ----
+struct HostMesh {
+	uint32_t nV = 0, nT = 0;
+	std::vector<double> X0;       // 3*nV, after autoResize
+	std::vector<float> w;         // inverse lumped masses
+	std::vector<uint8_t> flags;
+	std::vector<uint32_t> idx;    // 4*nT, stream order
+	std::vector<float> Qi, QQ, QR, volume, area; // 9/3/3/1/1 per element, stream order
+	std::vector<uint32_t> color;  // per element (stream order)
+	std::vector<uint32_t> order;  // equivalent serial order (colour-major, index-minor)
+	std::vector<uint32_t> colorStart; // nColors + 1 offsets into `order`
+	float origin[3] = { 0.0f, 0.0f, 0.0f };
+};
+
+// Returns 0 or an xf_status; on failure `err` holds the message.
+int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density,
+                bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err);
+int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
+                      std::string* err);
+
+// ---- kernel launchers (xf_kernels.cu) ----
+cudaError_t QueryLaunchShape(int device, uint32_t energy, bool exact, LaunchShape* shape);
+cudaError_t LaunchSubstepsPerColor(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, cudaStream_t stream,
+                                   uint64_t* launchCount);
+cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
+                                     cudaStream_t stream, uint64_t* launchCount);
+cudaError_t LaunchElementVolumes(const DeviceScene& sc, cudaStream_t stream, uint64_t* launchCount);  // -> sc.eScratch, stream order
+cudaError_t LaunchTransform(const DeviceScene& sc, const float* m9, cudaStream_t stream, uint64_t* launchCount);
+cudaError_t LaunchStats(const DeviceScene& sc, const SubstepParams& p, double gx, double gy, int smCount, cudaStream_t stream,
+                        uint64_t* launchCount);  // -> sc.statScratch[6]
+cudaError_t LaunchPackState(const DeviceScene& sc, double* dX, double* dV, float* dW, cudaStream_t stream, uint64_t* launchCount);
+cudaError_t LaunchUnpackState(const DeviceScene& sc, const double* dX, const double* dV, const float* dW, cudaStream_t stream,
+                              uint64_t* launchCount);
+
+}  // namespace xf
