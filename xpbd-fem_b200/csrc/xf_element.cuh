@@ -19,6 +19,10 @@
 
 namespace xf {
 
+// x / y where x is a per-call constant that is exactly +0 at nu == 0.5 (1/lambda): 0 / y == +0 for y > 0, so the
+// IEEE division (and its slow-path call for zero numerators) can be skipped without changing a bit.
+#define XF_DIV_MAYBE_ZERO(O, x, y) (((x) == 0.0f && (y) > 0.0f) ? 0.0f : O::div((x), (y)))
+
 template <bool EXACT>
 struct Op {
 	static __device__ __forceinline__ float mul(float a, float b) { if (EXACT) { return __fmul_rn(a, b); } else { return a * b; } }
@@ -247,7 +251,7 @@ template <bool EXACT, bool DAMPED>
 __device__ __forceinline__ void ConstrainOne(const DeviceScene& sc, const SubstepParams& p, const uint4& idx, VertexRegs (&v)[4], float U,
                                              const float (&g)[4][3], float compliance, float dampingGamma) {
 	typedef Op<EXACT> O;
-	float alpha = O::div(compliance, p.dt2);
+	float alpha = XF_DIV_MAYBE_ZERO(O, compliance, p.dt2);
 	float wgg = 1.0e-22f;
 #pragma unroll
 	for (int n = 0; n < 4; n++) { wgg = O::add(wgg, O::mul(v[n].w, O::dot(g[n], g[n]))); }
@@ -304,7 +308,7 @@ __device__ __forceinline__ void ConstrainBoth(const DeviceScene& sc, const Subst
                                               float dampingGamma) {
 	typedef Op<EXACT> O;
 	float alpha0 = O::div(comp0, p.dt2);
-	float alpha1 = O::div(comp1, p.dt2);
+	float alpha1 = XF_DIV_MAYBE_ZERO(O, comp1, p.dt2);
 	float w00 = 1.0e-22f, w10 = 1.0e-22f, w11 = 1.0e-22f;
 #pragma unroll
 	for (int n = 0; n < 4; n++) { w00 = O::add(w00, O::mul(v[n].w, O::dot(g0[n], g0[n]))); }
@@ -359,7 +363,8 @@ __device__ __forceinline__ void ConstrainBoth(const DeviceScene& sc, const Subst
 	for (int n = 0; n < 4; n++) {
 #pragma unroll
 		for (int k = 0; k < 3; k++) {
-			float acc = O::add(O::add(0.0f, O::mul(l0, g0[n][k])), O::mul(l1, g1[n][k]));
+			// Vec(0) + l0*g0 + l1*g1: the leading "+ 0" only normalises -0, which X += (double)... cannot observe
+			float acc = O::add(O::mul(l0, g0[n][k]), O::mul(l1, g1[n][k]));
 			v[n].x[k] = O::dadd(v[n].x[k], (double)O::mul(v[n].w, acc));
 		}
 	}
@@ -418,7 +423,7 @@ __device__ __forceinline__ void SolveElement(const DeviceScene& sc, const Subste
 #pragma unroll
 	for (int n = 0; n < 4; n++) { v[n] = LoadVertex(sc.Xw, is[n]); }
 	float comp0 = O::div(p.invMu, e.volume);
-	float comp1 = O::div(p.invLambda, e.volume);
+	float comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, e.volume);
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
 	float U0, U1;
 	bool haveF;
@@ -474,7 +479,7 @@ __device__ __forceinline__ void DampElement(const DeviceScene& sc, const Substep
 		for (int k = 0; k < 3; k++) { fv[n][k] = __double2float_rn(vel[n][k]); }
 	}
 	float comp0 = O::div(p.invMu, e.volume);
-	float comp1 = O::div(p.invLambda, e.volume);
+	float comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, e.volume);
 	float dg = p.dampDamping;
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
 	float U0, U1;

@@ -97,18 +97,24 @@ __global__ void __launch_bounds__(256) k_vertex_phase(const DeviceScene sc, cons
 // Sweeps over one colour (elements [begin, end) of the colour-sorted planes).
 //   KIND 0: main constraint solve   KIND 1: volume-only pass   KIND 2: Rayleigh damp (V)   KIND 3: PBD damp (V)
 // ------------------------------------------------------------------------------------------------
-template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-__device__ __forceinline__ void SweepOne(const DeviceScene& sc, const SubstepParams& p, uint32_t e) {
+template <int KIND, int ENERGY, bool EXACT>
+__device__ __forceinline__ void SweepLoad(const DeviceScene& sc, uint32_t e, ElemRec& rec) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
-	if (KIND == 3) {
-		PbdDampElement<EXACT>(sc, p, e, __ldg(sc.eIdx + e));
-		return;
-	}
-	ElemRec rec;
+	if (KIND == 3) { rec.idx = __ldg(sc.eIdx + e); return; }
 	LoadElement<(KIND != 1) && kPrefactored, EXACT>(sc, e, rec);
+}
+template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__device__ __forceinline__ void SweepRun(const DeviceScene& sc, const SubstepParams& p, uint32_t e, const ElemRec& rec) {
 	if (KIND == 0) { SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(sc, p, rec); }
 	if (KIND == 1) { SolveVolumeOnly<EXACT>(sc, p, rec); }
 	if (KIND == 2) { DampElement<ENERGY, SIMUL, EXACT>(sc, p, rec); }
+	if (KIND == 3) { PbdDampElement<EXACT>(sc, p, e, rec.idx); }
+}
+template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__device__ __forceinline__ void SweepOne(const DeviceScene& sc, const SubstepParams& p, uint32_t e) {
+	ElemRec rec;
+	SweepLoad<KIND, ENERGY, EXACT>(sc, e, rec);
+	SweepRun<KIND, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e, rec);
 }
 
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
@@ -151,46 +157,81 @@ __device__ __forceinline__ void DampSlice(const SubstepParams& p, uint32_t nT, u
 	}
 }
 
+// One colour range [b, end) swept by the whole grid.  Work is dealt out in warp-sized chunks round-robin over
+// the CTAs (chunk k -> CTA k % gridDim, warp slot k / gridDim) so that a colour smaller than the grid still
+// loads every SM equally.  `rec` holds this thread's first element of the range, loaded before the barrier
+// that precedes the sweep; the record of the first element of [nb, nend) is loaded before returning, so its
+// HBM/L2 latency overlaps the next barrier.
+template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, int NEXT_KIND>
+__device__ __forceinline__ void SweepRange(const DeviceScene& sc, const SubstepParams& p, uint32_t b, uint32_t end, uint32_t slot, uint32_t gsize,
+                                           ElemRec& rec, uint32_t nb, uint32_t nend) {
+	uint32_t e = b + slot;
+	if (e < end) { SweepRun<KIND, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e, rec); }
+	for (e += gsize; e < end; e += gsize) { SweepOne<KIND, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e); }
+	if (NEXT_KIND >= 0 && nb + slot < nend) { SweepLoad<(NEXT_KIND < 0 ? 0 : NEXT_KIND), ENERGY, EXACT>(sc, nb + slot, rec); }
+}
+
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 __global__ void __launch_bounds__(256, 2) k_substeps_persistent(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps) {
+	cg::grid_group grid = cg::this_grid();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t gsize = gridDim.x * blockDim.x;
-	unsigned int target = 0;
+	// element slot: warp-sized chunks dealt round-robin over CTAs
+	const uint32_t slot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
 	const bool anyDamp = p.doDamp || p.doPbdDamp;
+	const uint32_t nC = p.nColors;
+	ElemRec rec;
 	for (uint32_t s = 0; s < nSubsteps; s++) {
-		// vertex phase: post of the previous substep (unless a damping sweep already closed it) + predict
+		// prefetch the first record of colour 0, then the vertex phase: post of the previous substep (unless a
+		// damping sweep already closed it) + predict
+		if (p.colorStart[0] + slot < p.colorStart[1]) { SweepLoad<0, ENERGY, EXACT>(sc, p.colorStart[0] + slot, rec); }
 		const bool fusePost = (s > 0) && !anyDamp;
 		for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, fusePost, true); }
-		GridBarrier(sc.barrier, target);
-		for (uint32_t c = 0; c < p.nColors; c++) {
-			const uint32_t end = p.colorStart[c + 1];
-			for (uint32_t e = p.colorStart[c] + gtid; e < end; e += gsize) { SweepOne<0, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e); }
-			GridBarrier(sc.barrier, target);
+		grid.sync();
+		for (uint32_t c = 0; c < nC; c++) {
+			const bool last = c + 1 == nC;
+			if (!last) {
+				SweepRange<0, ENERGY, SIMUL, EXACT, DAMPED, 0>(sc, p, p.colorStart[c], p.colorStart[c + 1], slot, gsize, rec, p.colorStart[c + 1], p.colorStart[c + 2]);
+			} else if (p.volumePasses > 0) {
+				SweepRange<0, ENERGY, SIMUL, EXACT, DAMPED, 1>(sc, p, p.colorStart[c], p.colorStart[c + 1], slot, gsize, rec, p.colorStart[0], p.colorStart[1]);
+			} else {
+				SweepRange<0, ENERGY, SIMUL, EXACT, DAMPED, -1>(sc, p, p.colorStart[c], p.colorStart[c + 1], slot, gsize, rec, 0, 0);
+			}
+			grid.sync();
 		}
 		for (uint32_t pass = 0; pass < p.volumePasses; pass++) {
-			for (uint32_t c = 0; c < p.nColors; c++) {
-				const uint32_t end = p.colorStart[c + 1];
-				for (uint32_t e = p.colorStart[c] + gtid; e < end; e += gsize) { SweepOne<1, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
-				GridBarrier(sc.barrier, target);
+			for (uint32_t c = 0; c < nC; c++) {
+				const bool last = (c + 1 == nC) && (pass + 1 == p.volumePasses);
+				const uint32_t nc = (c + 1) % nC;
+				if (!last) {
+					SweepRange<1, ENERGY, SIMUL, EXACT, false, 1>(sc, p, p.colorStart[c], p.colorStart[c + 1], slot, gsize, rec, p.colorStart[nc], p.colorStart[nc + 1]);
+				} else {
+					SweepRange<1, ENERGY, SIMUL, EXACT, false, -1>(sc, p, p.colorStart[c], p.colorStart[c + 1], slot, gsize, rec, 0, 0);
+				}
+				grid.sync();
 			}
 		}
 		if (anyDamp) {
 			for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, true, false); }
-			GridBarrier(sc.barrier, target);
+			grid.sync();
 			uint32_t lo, hi;
 			DampSlice(p, sc.nT, p.tickId + s, lo, hi);
 			if (p.doDamp) {
-				for (uint32_t c = 0; c < p.nColors; c++) {
+				for (uint32_t c = 0; c < nC; c++) {
 					const uint32_t b = max(p.colorStart[c], lo), end = min(p.colorStart[c + 1], hi);
-					for (uint32_t e = b + gtid; e < end; e += gsize) { SweepOne<2, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
-					if (b < end) { GridBarrier(sc.barrier, target); }
+					if (b < end) {
+						for (uint32_t e = b + slot; e < end; e += gsize) { SweepOne<2, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+						grid.sync();
+					}
 				}
 			}
 			if (p.doPbdDamp) {
-				for (uint32_t c = 0; c < p.nColors; c++) {
+				for (uint32_t c = 0; c < nC; c++) {
 					const uint32_t b = max(p.colorStart[c], lo), end = min(p.colorStart[c + 1], hi);
-					for (uint32_t e = b + gtid; e < end; e += gsize) { SweepOne<3, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
-					if (b < end) { GridBarrier(sc.barrier, target); }
+					if (b < end) {
+						for (uint32_t e = b + slot; e < end; e += gsize) { SweepOne<3, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+						grid.sync();
+					}
 				}
 			}
 		}
@@ -486,3 +527,83 @@ cudaError_t LaunchElementVolumes(const DeviceScene& sc, cudaStream_t stream, uin
 }
 
 }  // namespace xf
+
+// ------------------------------------------------------------------------------------------------
+// Debug/measurement hook (not part of the public header): cost of the bare grid barrier, several variants.
+// ------------------------------------------------------------------------------------------------
+namespace xf {
+template <int VARIANT>
+__device__ __forceinline__ void GridBarrierV(unsigned int* counter, unsigned int& target) {
+	__syncthreads();
+	target += gridDim.x;
+	if (threadIdx.x == 0) {
+		if (VARIANT == 0) {
+			__threadfence();
+			atomicAdd(counter, 1u);
+			while (LoadAcquire(counter) < target) { }
+			__threadfence();
+		} else if (VARIANT == 1) {
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+			while (LoadAcquire(counter) < target) { }
+		} else if (VARIANT == 2) {
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+			unsigned int v;
+			do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target);
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
+		} else if (VARIANT == 3) {
+			asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+			unsigned int v;
+			do {
+				asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+				if (v < target) { __nanosleep(40); }
+			} while (v < target);
+			asm volatile("fence.acq_rel.gpu;" ::: "memory");
+		}
+	}
+	__syncthreads();
+}
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 2) k_barrier_only(unsigned int* counter, uint32_t iterations) {
+	unsigned int target = 0;
+	if (VARIANT == 4) {
+		cg::grid_group g = cg::this_grid();
+		for (uint32_t i = 0; i < iterations; i++) { g.sync(); }
+	} else {
+		for (uint32_t i = 0; i < iterations; i++) { GridBarrierV<VARIANT>(counter, target); }
+	}
+}
+}  // namespace xf
+
+extern "C" int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int threads, uint32_t iterations, float* outUsPerBarrier) {
+	cudaSetDevice(device);
+	cudaDeviceProp prop;
+	cudaGetDeviceProperties(&prop, device);
+	unsigned int* counter = nullptr;
+	cudaMalloc(&counter, 128);
+	cudaEvent_t a, b;
+	cudaEventCreate(&a);
+	cudaEventCreate(&b);
+	float best = 1e30f;
+	const void* fn = nullptr;
+	switch (variant) {
+	case 0: fn = (const void*)xf::k_barrier_only<0>; break;
+	case 1: fn = (const void*)xf::k_barrier_only<1>; break;
+	case 2: fn = (const void*)xf::k_barrier_only<2>; break;
+	case 3: fn = (const void*)xf::k_barrier_only<3>; break;
+	default: fn = (const void*)xf::k_barrier_only<4>; break;
+	}
+	for (int rep = 0; rep < 5; rep++) {
+		cudaMemset(counter, 0, 128);
+		void* args[] = { (void*)&counter, (void*)&iterations };
+		cudaEventRecord(a);
+		cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(prop.multiProcessorCount * blocksPerSm), dim3(threads), args, 0, 0);
+		cudaEventRecord(b);
+		if (e != cudaSuccess || cudaEventSynchronize(b) != cudaSuccess) { cudaFree(counter); return -2; }
+		float ms = 0.0f;
+		cudaEventElapsedTime(&ms, a, b);
+		best = ms < best ? ms : best;
+	}
+	cudaFree(counter);
+	*outUsPerBarrier = best * 1000.0f / (float)iterations;
+	return 0;
+}
