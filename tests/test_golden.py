@@ -1,0 +1,96 @@
+"""Golden-vector tests.  tests/golden/*.npz were produced by executing the UNMODIFIED reference
+(oracle/gen_golden.py); they travel to the GPU box where /root/reference does not exist.
+
+* CPU (not gpu): the C restatement (oracle/xpbd_oracle.c) replays every fixture bit-exactly.
+* GPU: the CUDA path (XF_PRECISION_EXACT, both schedules) replays the colour-order fixtures bit-exactly
+  through the C ABI, and XF_PRECISION_FAST stays inside 1e-5 x bbox after 1 and 10 substeps wherever the
+  reference itself is stable to that level (nu < 0.5)."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from __graft_entry__ import ROOT, build, load_package
+from oracle import bindings as ob
+
+build()
+xf = load_package()
+FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+def load(path):
+    d = np.load(path)
+    st_o = ob.Settings.from_buffer_copy(d["settings"].tobytes())
+    st_x = xf.Settings.from_buffer_copy(d["settings"].tobytes())
+    return d, st_o, st_x
+
+
+def test_fixture_inventory():
+    assert len(FIXTURES) == 48
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-4] for p in FIXTURES])
+def test_oracle_replays_reference_goldens(path):
+    d, st, _ = load(path)
+    o = ob.OracleScene(d["nodes"], d["idx"], float(d["density"]), bool(d["auto_resize"]))
+    o.set_order(d["order"])
+    done = 0
+    for snap in d["snapshots"]:
+        o.substep(st, float(d["dt"]), int(snap) - done)
+        st.tickId += int(snap) - done
+        done = int(snap)
+        X, V, w = o.get_state()
+        assert np.array_equal(X, d["X_%d" % snap]), "X after %d substeps" % snap
+        assert np.array_equal(V, d["V_%d" % snap])
+    assert np.array_equal(w, d["w_final"])
+    assert np.float32(o.volume()) == d["volume_final"]
+
+
+COLOUR_FIXTURES = [p for p in FIXTURES if "_colour_" in os.path.basename(p)]
+
+
+def make_geo(d, precision, schedule):
+    base = os.path.basename(str(d.fid.name))
+    hint = None
+    if base.startswith("beamL"):
+        hint = xf.GenerateTetBlock(8, 2)[2]
+    elif base.startswith("boxL"):
+        hint = xf.GenerateTetBlock(8, 8)[2]
+    geo = xf.GeoLinear3dCuda(d["nodes"], d["idx"], density=float(d["density"]), auto_resize=bool(d["auto_resize"]),
+                             precision=precision, schedule=schedule, color_hint=hint)
+    if not np.array_equal(geo.get_order(), d["order"]):
+        pytest.fail("the colouring changed since the fixtures were generated: re-run oracle/gen_golden.py in the build container")
+    return geo
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", [xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR])
+@pytest.mark.parametrize("path", COLOUR_FIXTURES, ids=[os.path.basename(p)[:-4] for p in COLOUR_FIXTURES])
+def test_cuda_exact_replays_reference_goldens(path, schedule):
+    d, _, st = load(path)
+    geo = make_geo(d, xf.PRECISION_EXACT, schedule)
+    done = 0
+    for snap in d["snapshots"]:
+        geo.Substep(st, float(d["dt"]), int(snap) - done)
+        st.tickId += int(snap) - done
+        done = int(snap)
+        X, V, w = geo.get_state()
+        assert np.array_equal(X, d["X_%d" % snap]), "X after %d substeps" % snap
+        assert np.array_equal(V, d["V_%d" % snap])
+    assert np.array_equal(w, d["w_final"])
+    assert np.float32(geo.CalculateVolume()) == d["volume_final"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", [p for p in COLOUR_FIXTURES if "nu0p5." not in p],
+                         ids=[os.path.basename(p)[:-4] for p in COLOUR_FIXTURES if "nu0p5." not in p])
+def test_cuda_fast_within_tolerance_of_reference_goldens(path):
+    d, _, st = load(path)
+    geo = make_geo(d, xf.PRECISION_FAST, xf.SCHEDULE_PERSISTENT)
+    bbox = (d["X_1"].max(0) - d["X_1"].min(0)).max()
+    geo.Substep(st, float(d["dt"]), 1)
+    assert np.abs(geo.get_state()[0] - d["X_1"]).max() / bbox < 1e-5  # north_star tolerance, per substep
+    geo.Substep(st, float(d["dt"]), 9)
+    assert np.abs(geo.get_state()[0] - d["X_10"]).max() / bbox < 1e-5
