@@ -195,6 +195,28 @@ typedef struct xf_info {
 } xf_info;
 int xf_get_info(const xf_scene* scene, xf_info* out);
 
+/* ---- batched scenes (BASELINE config 3): nScenes independent instances of ONE rest mesh, each with its own
+ * state and Settings, e.g. a vector of RL environments.  The reference would hold them as nScenes Geo objects and
+ * call Geo::Substep on each (Sim::Update's `for geo` loop, Demo.cpp:86-88); here one call steps all of them, one
+ * thread group per scene with the scene resident in shared memory.  Scenes too large for shared memory are
+ * rejected with XF_ERR_UNSUPPORTED (use xf_create per scene).  State buffers are [scene][vertex][xyz]. ---- */
+typedef struct xf_batch xf_batch;
+int xf_batch_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream,
+                    uint32_t idxCount, uint32_t nScenes, xf_batch** outBatch);
+int xf_batch_destroy(xf_batch* batch);
+uint32_t xf_batch_scene_count(const xf_batch* batch);
+uint32_t xf_batch_vert_count(const xf_batch* batch);
+uint32_t xf_batch_element_count(const xf_batch* batch);
+uint32_t xf_batch_color_count(const xf_batch* batch);
+int xf_batch_get_order(const xf_batch* batch, uint32_t* order);
+int xf_batch_set_ground(xf_batch* batch, int enabled, float y0, float friction);
+/* settingsCount == 1 (shared) or == scene count.  Energy / solve mode / Rayleigh type must agree across scenes. */
+int xf_batch_substep(xf_batch* batch, const xf_settings* settings, uint32_t settingsCount, float dt, uint32_t n);
+int xf_batch_sync(xf_batch* batch);
+int xf_batch_get_state(xf_batch* batch, uint32_t firstScene, uint32_t count, double* X, double* V, float* w);
+int xf_batch_set_state(xf_batch* batch, uint32_t firstScene, uint32_t count, const double* X, const double* V, const float* w);
+int xf_batch_get_info(const xf_batch* batch, uint32_t* groupThreads, uint32_t* blockThreads, uint32_t* smemBytes, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,9 @@ EXPORTS = [
     "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_elements", "xf_substep",
     "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
+    "xf_batch_create", "xf_batch_destroy", "xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count",
+    "xf_batch_color_count", "xf_batch_get_order", "xf_batch_set_ground", "xf_batch_substep", "xf_batch_sync",
+    "xf_batch_get_state", "xf_batch_set_state", "xf_batch_get_info",
 ]
 
 
@@ -148,6 +151,18 @@ def lib():
     L.xf_volume.argtypes = [vp, C.POINTER(f32)]
     L.xf_stats.argtypes = [vp, vp, vp]
     L.xf_get_info.argtypes = [vp, C.POINTER(Info)]
+    L.xf_batch_create.argtypes = [C.POINTER(CreateParams), vp, u32, vp, u32, u32, C.POINTER(vp)]
+    L.xf_batch_destroy.argtypes = [vp]
+    for n in ("xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count", "xf_batch_color_count"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = u32
+    L.xf_batch_get_order.argtypes = [vp, vp]
+    L.xf_batch_set_ground.argtypes = [vp, i32, f32, f32]
+    L.xf_batch_substep.argtypes = [vp, vp, u32, f32, u32]
+    L.xf_batch_sync.argtypes = [vp]
+    L.xf_batch_get_state.argtypes = [vp, u32, u32, vp, vp, vp]
+    L.xf_batch_set_state.argtypes = [vp, u32, u32, vp, vp, vp]
+    L.xf_batch_get_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -317,3 +332,81 @@ class GeoLinear3dCuda:
 
     def set_state_async(self, X_ptr, V_ptr):
         _check(lib().xf_set_state_async(self._h, X_ptr, V_ptr))
+
+
+class GeoBatchCuda:
+    """nScenes independent instances of one rest mesh (Sim::Update's `for geo` loop in one launch)."""
+
+    def __init__(self, nodes, idx_stream, n_scenes, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
+                 color_hint=None, stream=None):
+        L = lib()
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        p = CreateParams()
+        L.xf_default_create_params(C.byref(p))
+        p.device = device
+        p.density = density
+        p.autoResize = 1 if auto_resize else 0
+        p.precision = precision
+        p.stream = stream
+        if color_hint is not None:
+            color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)
+            p.colorHint = color_hint.ctypes.data
+            p.colorHintCount = color_hint.size
+        h = C.c_void_p()
+        self._h = None
+        _check(L.xf_batch_create(C.byref(p), _vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, int(n_scenes), C.byref(h)))
+        self._h = h
+        self.nScenes = L.xf_batch_scene_count(h)
+        self.nV = L.xf_batch_vert_count(h)
+        self.nT = L.xf_batch_element_count(h)
+        self.nColors = L.xf_batch_color_count(h)
+
+    def close(self):
+        if self._h:
+            lib().xf_batch_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_order(self):
+        o = np.empty(self.nT, dtype=np.uint32)
+        _check(lib().xf_batch_get_order(self._h, _vp(o)))
+        return o
+
+    def set_ground(self, enabled, y0=0.0, friction=0.0):
+        _check(lib().xf_batch_set_ground(self._h, 1 if enabled else 0, y0, friction))
+
+    def Substep(self, settings, dt, n=1):
+        """settings: one Settings (shared) or a ctypes array (Settings * nScenes)."""
+        if isinstance(settings, Settings):
+            _check(lib().xf_batch_substep(self._h, C.byref(settings), 1, float(dt), int(n)))
+        else:
+            _check(lib().xf_batch_substep(self._h, C.byref(settings), len(settings), float(dt), int(n)))
+
+    def Sync(self):
+        _check(lib().xf_batch_sync(self._h))
+
+    def get_state(self, first=0, count=None):
+        count = self.nScenes - first if count is None else count
+        X = np.empty((count, self.nV, 3), dtype=np.float64)
+        V = np.empty((count, self.nV, 3), dtype=np.float64)
+        w = np.empty((count, self.nV), dtype=np.float32)
+        _check(lib().xf_batch_get_state(self._h, first, count, _vp(X), _vp(V), _vp(w)))
+        return X, V, w
+
+    def set_state(self, first, X=None, V=None, w=None):
+        X = None if X is None else np.ascontiguousarray(X, dtype=np.float64)
+        V = None if V is None else np.ascontiguousarray(V, dtype=np.float64)
+        w = None if w is None else np.ascontiguousarray(w, dtype=np.float32)
+        count = (X if X is not None else V if V is not None else w).shape[0]
+        _check(lib().xf_batch_set_state(self._h, first, count, _vp(X), _vp(V), _vp(w)))
+
+    def info(self):
+        g, b, s, l = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().xf_batch_get_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(l)))
+        return dict(groupThreads=g.value, blockThreads=b.value, smemBytes=s.value, launches=l.value)

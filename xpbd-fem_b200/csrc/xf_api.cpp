@@ -10,9 +10,10 @@
 using namespace xf;
 
 namespace {
-
 thread_local std::string g_lastError;
+}
 
+namespace xf {
 int Fail(int status, const std::string& msg) {
 	g_lastError = msg;
 	return status;
@@ -21,6 +22,9 @@ int FailCuda(cudaError_t e, const char* what) {
 	g_lastError = std::string(what) + ": " + cudaGetErrorString(e);
 	return XF_ERR_CUDA;
 }
+}  // namespace xf
+
+namespace {
 #define XF_CUDA(call)                                                \
 	do {                                                             \
 		cudaError_t _e = (call);                                     \

@@ -1,0 +1,471 @@
+// Batched scenes (BASELINE config 3, "RL-env style"): nScenes independent instances of ONE rest mesh, each with
+// its own state (X, V, w) and its own Settings.  A group of T threads (T = 8..256, sub-warp groups for tiny
+// meshes) owns one scene for the whole call: the scene's vertices live in shared memory, the colour sweep is
+// separated by __syncwarp/__syncthreads instead of grid barriers, and the element records — identical for
+// every scene — are read through the read-only path and stay L1/L2 resident.  There is no HBM traffic per
+// substep at all; the kernel is bound by instruction issue/latency.  Results per scene are bit-identical
+// (XF_PRECISION_EXACT) to a single-scene run, i.e. to the reference's serial sweep in the colour order.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "xf_dispatch.cuh"
+#include "xf_element.cuh"
+
+namespace xf {
+
+struct BatchDevice {
+	uint32_t nScenes, nV, nT, nColors;
+	DeviceScene mesh;      // element planes + X0 of the shared rest mesh (vertex arrays unused)
+	const uint8_t* flags;  // nV
+	double* X;             // nScenes * 3 * nV
+	double* V;             // nScenes * 3 * nV
+	float* W;              // nScenes * nV
+	const SceneConsts* consts; // nScenes
+	uint32_t colorStart[kMaxColors + 1];
+};
+
+template <bool EXACT>
+__device__ __forceinline__ void BatchVertexPhase(const SmemStore& st, const BatchDevice& bd, const SceneConsts& p, uint32_t i, bool doPost,
+                                                 bool doPredict) {
+	typedef Op<EXACT> O;
+	VertexRegs v = st.LoadX(i);
+	double o[3], vel[3];
+	st.LoadO(i, o);
+	const uint32_t flags = bd.flags[i];
+	if (doPost) {
+		if (p.groundOn) {
+			double y0 = (double)p.groundY;
+			if (v.x[1] < y0) {
+				double keepT = (double)p.groundKeep;
+				v.x[1] = y0;
+				v.x[0] = O::dadd(o[0], O::dmul(O::dsub(v.x[0], o[0]), keepT));
+				v.x[2] = O::dadd(o[2], O::dmul(O::dsub(v.x[2], o[2]), keepT));
+			}
+		}
+		if (p.lockLeft && (flags & XF_VERT_LEFT)) {
+			v.x[0] = o[0]; v.x[1] = o[1]; v.x[2] = o[2];
+			v.w = 0.0f;
+		}
+		if (p.lockRight && (flags & XF_VERT_RIGHT)) {
+			double x0d[3];
+			LoadD3(bd.mesh.X0, i, x0d);
+			float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
+#pragma unroll
+			for (int r = 0; r < 3; r++) {
+				float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
+				double q = (double)O::add(p.origin[r], t);
+				v.x[r] = q;
+				o[r] = q;
+			}
+			v.w = 0.0f;
+		}
+		double invDt = (double)p.invDt;
+#pragma unroll
+		for (int k = 0; k < 3; k++) { vel[k] = O::dmul(O::dsub(v.x[k], o[k]), invDt); }
+	} else {
+		st.LoadV(i, vel);
+	}
+	if (doPredict) {
+		double g[3] = { (double)p.gdtX, (double)p.gdtY, 0.0 };
+		double keep = (double)p.keep;
+		double ddt = (double)p.dt;
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			vel[k] = O::dadd(vel[k], g[k]);
+			vel[k] = O::dmul(vel[k], keep);
+			o[k] = v.x[k];
+			v.x[k] = O::dadd(v.x[k], O::dmul(vel[k], ddt));
+		}
+	}
+	st.StoreX(i, v);
+	st.w[i] = v.w;
+	st.O[3 * i] = o[0]; st.O[3 * i + 1] = o[1]; st.O[3 * i + 2] = o[2];
+	st.StoreV(i, vel);
+}
+
+__device__ __forceinline__ void GroupSync(uint32_t groupThreads) {
+	if (groupThreads <= 32) { __syncwarp(); } else { __syncthreads(); }
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__global__ void __launch_bounds__(256) k_batch_substeps(const __grid_constant__ BatchDevice bd, uint32_t nSubsteps, uint32_t groupThreads) {
+	extern __shared__ double smemRaw[];
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	const uint32_t T = groupThreads;
+	const uint32_t groupsPerBlock = blockDim.x / T;
+	const uint32_t g = threadIdx.x / T, t = threadIdx.x % T;
+	const uint32_t nV = bd.nV, n3 = 3 * nV;
+	const uint32_t perGroupDoubles = 3 * n3 + (nV + 1) / 2;
+	SmemStore st;
+	st.X = smemRaw + (size_t)g * perGroupDoubles;
+	st.O = st.X + n3;
+	st.V = st.O + n3;
+	st.w = reinterpret_cast<float*>(st.V + n3);
+	const uint32_t stride = gridDim.x * groupsPerBlock;
+	const uint32_t rounds = (bd.nScenes + stride - 1) / stride;
+	for (uint32_t round = 0; round < rounds; round++) {
+		const uint32_t scene = round * stride + blockIdx.x * groupsPerBlock + g;
+		const bool active = scene < bd.nScenes;
+		const SceneConsts& p = bd.consts[active ? scene : 0];
+		if (active) {
+			const double* gx = bd.X + (size_t)scene * n3;
+			const double* gv = bd.V + (size_t)scene * n3;
+			for (uint32_t i = t; i < n3; i += T) { st.X[i] = gx[i]; st.O[i] = gx[i]; st.V[i] = gv[i]; }
+			for (uint32_t i = t; i < nV; i += T) { st.w[i] = bd.W[(size_t)scene * nV + i]; }
+		}
+		GroupSync(T);
+		const bool anyDamp = p.doDamp || p.doPbdDamp;
+		for (uint32_t s = 0; s < nSubsteps; s++) {
+			if (active) {
+				const bool fusePost = (s > 0) && !anyDamp;
+				for (uint32_t i = t; i < nV; i += T) { BatchVertexPhase<EXACT>(st, bd, p, i, fusePost, true); }
+			}
+			GroupSync(T);
+			for (uint32_t c = 0; c < bd.nColors; c++) {
+				if (active) {
+					for (uint32_t e = bd.colorStart[c] + t; e < bd.colorStart[c + 1]; e += T) {
+						ElemRec rec;
+						LoadElement<kPrefactored, EXACT>(bd.mesh, e, rec);
+						SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(st, p, rec);
+					}
+				}
+				GroupSync(T);
+			}
+			for (uint32_t pass = 0; pass < p.volumePasses; pass++) {
+				for (uint32_t c = 0; c < bd.nColors; c++) {
+					if (active) {
+						for (uint32_t e = bd.colorStart[c] + t; e < bd.colorStart[c + 1]; e += T) {
+							ElemRec rec;
+							LoadElement<false, EXACT>(bd.mesh, e, rec);
+							SolveVolumeOnly<EXACT>(st, p, rec);
+						}
+					}
+					GroupSync(T);
+				}
+			}
+			if (anyDamp) {
+				if (active) {
+					for (uint32_t i = t; i < nV; i += T) { BatchVertexPhase<EXACT>(st, bd, p, i, true, false); }
+				}
+				GroupSync(T);
+				uint32_t lo = 0, hi = bd.nT;
+				if (p.rayleigh == XF_RAYLEIGH_POST_AMORTIZED) {
+					uint32_t k = (p.tickId + s) % XF_AMORTIZATION_PERIOD;
+					lo = (uint32_t)(((uint64_t)bd.nT * k) / XF_AMORTIZATION_PERIOD);
+					hi = (uint32_t)(((uint64_t)bd.nT * (k + 1)) / XF_AMORTIZATION_PERIOD);
+				}
+				if (p.doDamp) {
+					for (uint32_t c = 0; c < bd.nColors; c++) {
+						const uint32_t b = max(bd.colorStart[c], lo), end = min(bd.colorStart[c + 1], hi);
+						if (active) {
+							for (uint32_t e = b + t; e < end; e += T) {
+								ElemRec rec;
+								LoadElement<kPrefactored, EXACT>(bd.mesh, e, rec);
+								DampElement<ENERGY, SIMUL, EXACT>(st, p, rec);
+							}
+						}
+						GroupSync(T);
+					}
+				}
+				if (p.doPbdDamp) {
+					for (uint32_t c = 0; c < bd.nColors; c++) {
+						const uint32_t b = max(bd.colorStart[c], lo), end = min(bd.colorStart[c + 1], hi);
+						if (active) {
+							for (uint32_t e = b + t; e < end; e += T) { PbdDampElement<EXACT>(st, p, __ldg(bd.mesh.eArea + e), __ldg(bd.mesh.eIdx + e)); }
+						}
+						GroupSync(T);
+					}
+				}
+			}
+		}
+		if (active) {
+			if (!anyDamp && nSubsteps > 0) {
+				for (uint32_t i = t; i < nV; i += T) { BatchVertexPhase<EXACT>(st, bd, p, i, true, false); }
+			}
+		}
+		GroupSync(T);
+		if (active) {
+			double* gx = bd.X + (size_t)scene * n3;
+			double* gv = bd.V + (size_t)scene * n3;
+			for (uint32_t i = t; i < n3; i += T) { gx[i] = st.X[i]; gv[i] = st.V[i]; }
+			for (uint32_t i = t; i < nV; i += T) { bd.W[(size_t)scene * nV + i] = st.w[i]; }
+		}
+		GroupSync(T);
+	}
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct BatchRunner {
+	static cudaError_t Run(const BatchDevice& bd, uint32_t nSubsteps, uint32_t groupThreads, uint32_t blockThreads, size_t smemBytes, int smCount,
+	                       cudaStream_t st) {
+		auto fn = k_batch_substeps<ENERGY, SIMUL, EXACT, DAMPED>;
+		cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes);
+		if (e != cudaSuccess) { return e; }
+		int perSm = 0;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, (int)blockThreads, smemBytes);
+		if (e != cudaSuccess) { return e; }
+		if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		const uint32_t groupsPerBlock = blockThreads / groupThreads;
+		uint32_t blocks = (bd.nScenes + groupsPerBlock - 1) / groupsPerBlock;
+		const uint32_t resident = (uint32_t)(perSm * smCount);
+		if (blocks > resident) { blocks = resident; } // persistent over rounds of scenes
+		fn<<<dim3(blocks), dim3(blockThreads), smemBytes, st>>>(bd, nSubsteps, groupThreads);
+		return cudaGetLastError();
+	}
+};
+
+}  // namespace xf
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace xf;
+
+struct xf_batch {
+	HostMesh mesh;
+	BatchDevice dev;
+	int device = 0;
+	int precision = XF_PRECISION_EXACT;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	int smCount = 0;
+	size_t maxSmem = 0;
+	uint32_t groupThreads = 32, blockThreads = 128;
+	size_t smemBytes = 0;
+	uint32_t groundOn = 0;
+	float groundY = 0.0f, groundFriction = 0.0f;
+	SceneConsts* dConsts = nullptr;
+	uint8_t* dFlags = nullptr;
+	std::vector<SceneConsts> hConsts;
+	uint64_t launches = 0;
+};
+
+#define XFB_CUDA(call)                                         \
+	do {                                                       \
+		cudaError_t _e = (call);                               \
+		if (_e != cudaSuccess) { return FailCuda(_e, #call); } \
+	} while (0)
+
+namespace {
+template <typename T>
+cudaError_t UploadVec(T** dst, const std::vector<T>& src) {
+	cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * std::max<size_t>(src.size(), 1));
+	if (e != cudaSuccess) { return e; }
+	return cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+}
+void FreeBatch(xf_batch* b) {
+	cudaSetDevice(b->device);
+	DeviceScene& d = b->dev.mesh;
+	void* ptrs[] = { d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, d.eArea, b->dev.X, b->dev.V, b->dev.W, b->dConsts, b->dFlags };
+	for (void* p : ptrs) { if (p) { cudaFree(p); } }
+	if (b->ownStream && b->stream) { cudaStreamDestroy(b->stream); }
+}
+}  // namespace
+
+extern "C" {
+
+int xf_batch_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount,
+                    uint32_t nScenes, xf_batch** outBatch) {
+	if (!params || !outBatch || nScenes == 0) { return Fail(XF_ERR_INVALID, "null params/outBatch or zero scenes"); }
+	*outBatch = nullptr;
+	if (params->abiVersion != XF_ABI_VERSION) { return Fail(XF_ERR_INVALID, "xf_create_params.abiVersion mismatch"); }
+	if (params->device < 0) { return Fail(XF_ERR_CUDA, "a batch needs a CUDA device: there is no CPU compute path"); }
+	xf_batch* b = new (std::nothrow) xf_batch();
+	if (!b) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
+	std::string err;
+	int rc = PrepareMesh(nodeXYZ, nodeFloatCount, idxStream, idxCount, params->density, params->autoResize != 0, params->colorHint,
+	                     params->colorHintCount, &b->mesh, &err);
+	if (rc != XF_OK) { delete b; return Fail(rc, err); }
+	b->device = params->device;
+	b->precision = params->precision;
+	cudaError_t e = cudaSetDevice(b->device);
+	if (e != cudaSuccess) { delete b; return FailCuda(e, "cudaSetDevice"); }
+	cudaDeviceProp prop;
+	e = cudaGetDeviceProperties(&prop, b->device);
+	if (e != cudaSuccess) { delete b; return FailCuda(e, "cudaGetDeviceProperties"); }
+	b->smCount = prop.multiProcessorCount;
+	b->maxSmem = prop.sharedMemPerBlockOptin;
+	const HostMesh& m = b->mesh;
+	// group size: the smallest power of two that covers the largest colour, 8..256
+	uint32_t maxColor = 0;
+	for (size_t c = 0; c + 1 < m.colorStart.size(); c++) { maxColor = std::max(maxColor, m.colorStart[c + 1] - m.colorStart[c]); }
+	uint32_t T = 8;
+	while (T < maxColor && T < 256) { T *= 2; }
+	const size_t perGroup = sizeof(double) * (9 * (size_t)m.nV + (m.nV + 1) / 2);
+	if (perGroup > b->maxSmem) {
+		delete b;
+		return Fail(XF_ERR_UNSUPPORTED, "scene too large for the shared-memory batch path (" + std::to_string(m.nV) +
+		                                    " vertices); create individual scenes with xf_create instead");
+	}
+	uint32_t blockThreads = std::max<uint32_t>(T, 128);
+	while (blockThreads > T && (blockThreads / T) * perGroup > b->maxSmem) { blockThreads /= 2; }
+	if (blockThreads < 32) { blockThreads = 32; }
+	b->groupThreads = T;
+	b->blockThreads = blockThreads;
+	b->smemBytes = (blockThreads / T) * perGroup;
+	if (params->stream) { b->stream = (cudaStream_t)params->stream; }
+	else {
+		e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+		if (e != cudaSuccess) { delete b; return FailCuda(e, "cudaStreamCreate"); }
+		b->ownStream = true;
+	}
+	BatchDevice& d = b->dev;
+	memset(&d, 0, sizeof(d));
+	d.nScenes = nScenes;
+	d.nV = m.nV;
+	d.nT = m.nT;
+	d.nColors = (uint32_t)m.colorStart.size() - 1;
+	for (size_t c = 0; c < m.colorStart.size(); c++) { d.colorStart[c] = m.colorStart[c]; }
+	d.mesh.nV = m.nV;
+	d.mesh.nT = m.nT;
+	std::vector<uint4> eIdx(m.nT);
+	std::vector<float4> q0(m.nT), q1(m.nT), c0(m.nT);
+	std::vector<float2> q2(m.nT), c1(m.nT);
+	std::vector<float> area(m.nT);
+	for (uint32_t pos = 0; pos < m.nT; pos++) {
+		const uint32_t el = m.order[pos];
+		const uint32_t* v = &m.idx[4 * (size_t)el];
+		const float* Q = &m.Qi[9 * (size_t)el];
+		eIdx[pos] = uint4{ v[0], v[1], v[2], v[3] };
+		q0[pos] = float4{ Q[0], Q[1], Q[2], Q[3] };
+		q1[pos] = float4{ Q[4], Q[5], Q[6], Q[7] };
+		q2[pos] = float2{ Q[8], m.volume[el] };
+		c0[pos] = float4{ m.QQ[3 * (size_t)el], m.QQ[3 * (size_t)el + 1], m.QQ[3 * (size_t)el + 2], m.QR[3 * (size_t)el] };
+		c1[pos] = float2{ m.QR[3 * (size_t)el + 1], m.QR[3 * (size_t)el + 2] };
+		area[pos] = m.area[el];
+	}
+	std::vector<double4> x0(m.nV);
+	for (uint32_t i = 0; i < m.nV; i++) { x0[i] = double4{ m.X0[3 * (size_t)i], m.X0[3 * (size_t)i + 1], m.X0[3 * (size_t)i + 2], 0.0 }; }
+	bool ok = UploadVec(&d.mesh.eIdx, eIdx) == cudaSuccess && UploadVec(&d.mesh.eQ0, q0) == cudaSuccess && UploadVec(&d.mesh.eQ1, q1) == cudaSuccess &&
+	          UploadVec(&d.mesh.eQ2, q2) == cudaSuccess && UploadVec(&d.mesh.eC0, c0) == cudaSuccess && UploadVec(&d.mesh.eC1, c1) == cudaSuccess &&
+	          UploadVec(&d.mesh.eArea, area) == cudaSuccess && UploadVec(&d.mesh.X0, x0) == cudaSuccess && UploadVec(&b->dFlags, m.flags) == cudaSuccess;
+	d.flags = b->dFlags;
+	const size_t n3 = 3 * (size_t)m.nV;
+	ok = ok && cudaMalloc((void**)&d.X, sizeof(double) * n3 * nScenes) == cudaSuccess && cudaMalloc((void**)&d.V, sizeof(double) * n3 * nScenes) == cudaSuccess &&
+	     cudaMalloc((void**)&d.W, sizeof(float) * m.nV * (size_t)nScenes) == cudaSuccess &&
+	     cudaMalloc((void**)&b->dConsts, sizeof(SceneConsts) * nScenes) == cudaSuccess;
+	if (!ok) { cudaError_t le = cudaGetLastError(); FreeBatch(b); delete b; return FailCuda(le, "batch allocation/upload"); }
+	d.consts = b->dConsts;
+	// every scene starts at the rest state
+	std::vector<double> X(n3 * nScenes);
+	std::vector<float> W((size_t)m.nV * nScenes);
+	for (uint32_t s = 0; s < nScenes; s++) {
+		memcpy(&X[n3 * s], m.X0.data(), sizeof(double) * n3);
+		memcpy(&W[(size_t)m.nV * s], m.w.data(), sizeof(float) * m.nV);
+	}
+	if (cudaMemcpy(d.X, X.data(), sizeof(double) * X.size(), cudaMemcpyHostToDevice) != cudaSuccess ||
+	    cudaMemset(d.V, 0, sizeof(double) * n3 * nScenes) != cudaSuccess ||
+	    cudaMemcpy(d.W, W.data(), sizeof(float) * W.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+		cudaError_t le = cudaGetLastError(); FreeBatch(b); delete b; return FailCuda(le, "batch state upload");
+	}
+	b->hConsts.resize(nScenes);
+	*outBatch = b;
+	return XF_OK;
+}
+
+int xf_batch_destroy(xf_batch* b) {
+	if (!b) { return XF_OK; }
+	cudaSetDevice(b->device);
+	if (b->stream) { cudaStreamSynchronize(b->stream); }
+	FreeBatch(b);
+	delete b;
+	return XF_OK;
+}
+
+uint32_t xf_batch_scene_count(const xf_batch* b) { return b ? b->dev.nScenes : 0; }
+uint32_t xf_batch_vert_count(const xf_batch* b) { return b ? b->mesh.nV : 0; }
+uint32_t xf_batch_element_count(const xf_batch* b) { return b ? b->mesh.nT : 0; }
+uint32_t xf_batch_color_count(const xf_batch* b) { return b ? (uint32_t)b->mesh.colorStart.size() - 1 : 0; }
+
+int xf_batch_get_order(const xf_batch* b, uint32_t* order) {
+	if (!b || !order) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(order, b->mesh.order.data(), sizeof(uint32_t) * b->mesh.nT);
+	return XF_OK;
+}
+
+int xf_batch_set_ground(xf_batch* b, int enabled, float y0, float friction) {
+	if (!b) { return Fail(XF_ERR_INVALID, "null batch"); }
+	b->groundOn = enabled ? 1u : 0u;
+	b->groundY = y0;
+	b->groundFriction = friction;
+	return XF_OK;
+}
+
+// settings: `settingsCount` == 1 (shared by all scenes) or == scene count (one per scene).  Energy, solve mode and
+// Rayleigh type select the kernel instantiation and must be the same for every scene.
+int xf_batch_substep(xf_batch* b, const xf_settings* settings, uint32_t settingsCount, float dt, uint32_t n) {
+	if (!b || !settings) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (settingsCount != 1 && settingsCount != b->dev.nScenes) { return Fail(XF_ERR_INVALID, "settingsCount must be 1 or the scene count"); }
+	if (n == 0) { return XF_OK; }
+	XFB_CUDA(cudaSetDevice(b->device));
+	SubstepParams p0;
+	bool damped0 = false;
+	for (uint32_t s = 0; s < b->dev.nScenes; s++) {
+		const xf_settings* st = &settings[settingsCount == 1 ? 0 : s];
+		if (s > 0 && settingsCount == 1) { b->hConsts[s] = b->hConsts[0]; continue; }
+		SubstepParams p;
+		std::string err;
+		int rc = FillSubstepParams(st, nullptr, dt, b->mesh, &p, &err);
+		if (rc != XF_OK) { return Fail(rc, "scene " + std::to_string(s) + ": " + err); }
+		const bool damped = p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST;
+		if (s == 0) { p0 = p; damped0 = damped; }
+		else if (p.energy != p0.energy || p.simultaneous != p0.simultaneous || p.rayleigh != p0.rayleigh || damped != damped0) {
+			return Fail(XF_ERR_UNSUPPORTED, "all scenes of a batch must share energy, solve mode and damping type (scene " + std::to_string(s) + " differs)");
+		}
+		SceneConsts& c = b->hConsts[s];
+		c.dt = p.dt; c.dt2 = p.dt2; c.invDt = p.invDt; c.gdtX = p.gdtX; c.gdtY = p.gdtY; c.keep = p.keep;
+		c.invMu = p.invMu; c.invLambda = p.invLambda; c.a = p.a; c.damping = p.damping; c.compliance = p.compliance;
+		c.pbdDamping = p.pbdDamping; c.dampDamping = p.dampDamping; c.rayleigh = p.rayleigh; c.lockLeft = p.lockLeft; c.lockRight = p.lockRight;
+		c.volumePasses = p.volumePasses; c.tickId = p.tickId; c.doDamp = p.doDamp; c.doPbdDamp = p.doPbdDamp;
+		memcpy(c.lockT, p.lockT, sizeof(c.lockT));
+		memcpy(c.origin, p.origin, sizeof(c.origin));
+		c.groundOn = b->groundOn; c.groundY = b->groundY; c.groundKeep = 1.0f - b->groundFriction;
+	}
+	XFB_CUDA(cudaMemcpyAsync(b->dConsts, b->hConsts.data(), sizeof(SceneConsts) * b->dev.nScenes, cudaMemcpyHostToDevice, b->stream));
+	XFB_CUDA(DispatchConfig<BatchRunner>(p0.energy, p0.simultaneous != 0, b->precision == XF_PRECISION_EXACT, damped0, b->dev, n, b->groupThreads,
+	                                     b->blockThreads, b->smemBytes, b->smCount, b->stream));
+	b->launches++;
+	return XF_OK;
+}
+
+int xf_batch_sync(xf_batch* b) {
+	if (!b) { return Fail(XF_ERR_INVALID, "null batch"); }
+	XFB_CUDA(cudaSetDevice(b->device));
+	XFB_CUDA(cudaStreamSynchronize(b->stream));
+	return XF_OK;
+}
+
+int xf_batch_get_state(xf_batch* b, uint32_t firstScene, uint32_t count, double* X, double* V, float* w) {
+	if (!b || firstScene + count > b->dev.nScenes) { return Fail(XF_ERR_INVALID, "scene range out of bounds"); }
+	XFB_CUDA(cudaSetDevice(b->device));
+	const size_t n3 = 3 * (size_t)b->mesh.nV;
+	if (X) { XFB_CUDA(cudaMemcpyAsync(X, b->dev.X + n3 * firstScene, sizeof(double) * n3 * count, cudaMemcpyDeviceToHost, b->stream)); }
+	if (V) { XFB_CUDA(cudaMemcpyAsync(V, b->dev.V + n3 * firstScene, sizeof(double) * n3 * count, cudaMemcpyDeviceToHost, b->stream)); }
+	if (w) { XFB_CUDA(cudaMemcpyAsync(w, b->dev.W + (size_t)b->mesh.nV * firstScene, sizeof(float) * b->mesh.nV * count, cudaMemcpyDeviceToHost, b->stream)); }
+	XFB_CUDA(cudaStreamSynchronize(b->stream));
+	return XF_OK;
+}
+
+int xf_batch_set_state(xf_batch* b, uint32_t firstScene, uint32_t count, const double* X, const double* V, const float* w) {
+	if (!b || firstScene + count > b->dev.nScenes) { return Fail(XF_ERR_INVALID, "scene range out of bounds"); }
+	XFB_CUDA(cudaSetDevice(b->device));
+	const size_t n3 = 3 * (size_t)b->mesh.nV;
+	if (X) { XFB_CUDA(cudaMemcpyAsync(b->dev.X + n3 * firstScene, X, sizeof(double) * n3 * count, cudaMemcpyHostToDevice, b->stream)); }
+	if (V) { XFB_CUDA(cudaMemcpyAsync(b->dev.V + n3 * firstScene, V, sizeof(double) * n3 * count, cudaMemcpyHostToDevice, b->stream)); }
+	if (w) { XFB_CUDA(cudaMemcpyAsync(b->dev.W + (size_t)b->mesh.nV * firstScene, w, sizeof(float) * b->mesh.nV * count, cudaMemcpyHostToDevice, b->stream)); }
+	XFB_CUDA(cudaStreamSynchronize(b->stream));
+	return XF_OK;
+}
+
+int xf_batch_get_info(const xf_batch* b, uint32_t* groupThreads, uint32_t* blockThreads, uint32_t* smemBytes, uint64_t* launches) {
+	if (!b) { return Fail(XF_ERR_INVALID, "null batch"); }
+	if (groupThreads) { *groupThreads = b->groupThreads; }
+	if (blockThreads) { *blockThreads = b->blockThreads; }
+	if (smemBytes) { *smemBytes = (uint32_t)b->smemBytes; }
+	if (launches) { *launches = b->launches; }
+	return XF_OK;
+}
+
+}  // extern "C"

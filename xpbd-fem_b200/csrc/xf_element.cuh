@@ -114,6 +114,38 @@ __device__ __forceinline__ void StoreD3(double4* A, uint32_t i, const double* v)
 	__stcg(p + 1, make_double2(v[2], 0.0));
 }
 
+// Vertex-store policies: where an element's vertices live.  GlobalStore = the HBM/L2 arrays of a DeviceScene
+// (one mesh per device); SmemStore = one small scene resident in shared memory (batched scenes, xf_batch.cu).
+struct GlobalStore {
+	VertexRec* Xw;
+	double4* O;
+	double4* V;
+	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return LoadVertex(Xw, i); }
+	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const { StoreVertex(Xw, i, v); }
+	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { LoadD3(O, i, o); }
+	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { LoadD3(V, i, o); }
+	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const { StoreD3(V, i, v); }
+};
+__device__ __forceinline__ GlobalStore StoreOf(const DeviceScene& sc) { return GlobalStore{ sc.Xw, sc.O, sc.V }; }
+
+struct SmemStore {
+	double* X; // 3 per vertex
+	double* O;
+	double* V;
+	float* w;
+	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const {
+		VertexRegs v;
+		v.x[0] = X[3 * i]; v.x[1] = X[3 * i + 1]; v.x[2] = X[3 * i + 2];
+		v.w = w[i];
+		v.flags = 0;
+		return v;
+	}
+	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const { X[3 * i] = v.x[0]; X[3 * i + 1] = v.x[1]; X[3 * i + 2] = v.x[2]; }
+	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { o[0] = O[3 * i]; o[1] = O[3 * i + 1]; o[2] = O[3 * i + 2]; }
+	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { o[0] = V[3 * i]; o[1] = V[3 * i + 1]; o[2] = V[3 * i + 2]; }
+	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const { V[3 * i] = v[0]; V[3 * i + 1] = v[1]; V[3 * i + 2] = v[2]; }
+};
+
 // P[n] = Vec(X[n] - X[3]): fp64 difference, then narrowed.  Fem.cpp:453
 template <bool EXACT>
 __device__ __forceinline__ void Edges(const VertexRegs (&v)[4], float (&P)[3][3]) {
@@ -234,21 +266,21 @@ __device__ __forceinline__ float YeohSlope(float IM) {
 }
 
 // (X[n] - O[n]) narrowed, for the in-constraint damping terms.  Xpbd.h:96, 139
-template <bool EXACT>
-__device__ __forceinline__ void Displacements(const DeviceScene& sc, const uint4& idx, const VertexRegs (&v)[4], float (&d)[4][3]) {
+template <bool EXACT, typename VS>
+__device__ __forceinline__ void Displacements(const VS& vs, const uint4& idx, const VertexRegs (&v)[4], float (&d)[4][3]) {
 	const uint32_t is[4] = { idx.x, idx.y, idx.z, idx.w };
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
 		double o[3];
-		LoadD3(sc.O, is[n], o);
+		vs.LoadO(is[n], o);
 #pragma unroll
 		for (int k = 0; k < 3; k++) { d[n][k] = __double2float_rn(Op<EXACT>::dsub(v[n].x[k], o[k])); }
 	}
 }
 
 // EnergyXpbdConstrain, Xpbd.h:86-120.  Updates the register copies of the positions.
-template <bool EXACT, bool DAMPED>
-__device__ __forceinline__ void ConstrainOne(const DeviceScene& sc, const SubstepParams& p, const uint4& idx, VertexRegs (&v)[4], float U,
+template <bool EXACT, bool DAMPED, typename VS, typename PARAMS>
+__device__ __forceinline__ void ConstrainOne(const VS& vs, const PARAMS& p, const uint4& idx, VertexRegs (&v)[4], float U,
                                              const float (&g)[4][3], float compliance, float dampingGamma) {
 	typedef Op<EXACT> O;
 	float alpha = XF_DIV_MAYBE_ZERO(O, compliance, p.dt2);
@@ -259,7 +291,7 @@ __device__ __forceinline__ void ConstrainOne(const DeviceScene& sc, const Subste
 	float twoU = O::mul(2.0f, U);
 	if (DAMPED) {
 		float d[4][3];
-		Displacements<EXACT>(sc, idx, v, d);
+		Displacements<EXACT>(vs, idx, v, d);
 		float gV = 0.0f;
 #pragma unroll
 		for (int n = 0; n < 4; n++) { gV = O::add(gV, O::dot(d[n], g[n])); }
@@ -302,8 +334,8 @@ __device__ __forceinline__ void Cramer2(float A0, float A1, float A2, float b0, 
 }
 
 // EnergyXpbdConstrainSimultaneous<.., 2>, Xpbd.h:122-214
-template <bool EXACT, bool DAMPED>
-__device__ __forceinline__ void ConstrainBoth(const DeviceScene& sc, const SubstepParams& p, const uint4& idx, VertexRegs (&v)[4], float U0,
+template <bool EXACT, bool DAMPED, typename VS, typename PARAMS>
+__device__ __forceinline__ void ConstrainBoth(const VS& vs, const PARAMS& p, const uint4& idx, VertexRegs (&v)[4], float U0,
                                               float U1, const float (&g0)[4][3], const float (&g1)[4][3], float comp0, float comp1,
                                               float dampingGamma) {
 	typedef Op<EXACT> O;
@@ -321,7 +353,7 @@ __device__ __forceinline__ void ConstrainBoth(const DeviceScene& sc, const Subst
 	float gamma = 0.0f;
 	if (DAMPED) {
 		float d[4][3];
-		Displacements<EXACT>(sc, idx, v, d);
+		Displacements<EXACT>(vs, idx, v, d);
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
 			gV0 = O::add(gV0, O::dot(g0[n], d[n]));
@@ -415,13 +447,13 @@ __device__ __forceinline__ void DeviatoricTerm(const ElemRec& e, const float (&P
 }
 
 // One element of GeoLinear3d::Constrain's main sweep.
-template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-__device__ __forceinline__ void SolveElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& e) {
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
+__device__ __forceinline__ void SolveElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
 	VertexRegs v[4];
 #pragma unroll
-	for (int n = 0; n < 4; n++) { v[n] = LoadVertex(sc.Xw, is[n]); }
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); }
 	float comp0 = O::div(p.invMu, e.volume);
 	float comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, e.volume);
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
@@ -432,40 +464,40 @@ __device__ __forceinline__ void SolveElement(const DeviceScene& sc, const Subste
 	if (SIMUL) {
 		if (!(ENERGY == XF_ENERGY_MIXED || ENERGY == XF_ENERGY_YEOH_SKIN)) { DeformationGradient<EXACT>(e, P, F); }
 		U1 = VolumetricFromF<EXACT>(e, F, p.a, g1);
-		ConstrainBoth<EXACT, DAMPED>(sc, p, e.idx, v, U0, U1, g0, g1, comp0, comp1, p.damping);
+		ConstrainBoth<EXACT, DAMPED>(vs, p, e.idx, v, U0, U1, g0, g1, comp0, comp1, p.damping);
 	} else {
-		ConstrainOne<EXACT, DAMPED>(sc, p, e.idx, v, U0, g0, comp0, p.damping);
+		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U0, g0, comp0, p.damping);
 		Edges<EXACT>(v, P);
 		DeformationGradient<EXACT>(e, P, F);
 		U1 = VolumetricFromF<EXACT>(e, F, p.a, g1);
-		ConstrainOne<EXACT, DAMPED>(sc, p, e.idx, v, U1, g1, comp1, p.damping);
+		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U1, g1, comp1, p.damping);
 	}
 #pragma unroll
-	for (int n = 0; n < 4; n++) { StoreVertex(sc.Xw, is[n], v[n]); }
+	for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
 }
 
 // SolveVolumeOnly, Fem.cpp:840-867 (J -> 1 with compliance * volume, never damped).
-template <bool EXACT>
-__device__ __forceinline__ void SolveVolumeOnly(const DeviceScene& sc, const SubstepParams& p, const ElemRec& e) {
+template <bool EXACT, typename VS, typename PARAMS>
+__device__ __forceinline__ void SolveVolumeOnly(const VS& vs, const PARAMS& p, const ElemRec& e) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
 	VertexRegs v[4];
 #pragma unroll
-	for (int n = 0; n < 4; n++) { v[n] = LoadVertex(sc.Xw, is[n]); }
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); }
 	float comp = O::mul(p.compliance, e.volume);
 	float P[3][3], F[3][3], g[4][3];
 	Edges<EXACT>(v, P);
 	DeformationGradient<EXACT>(e, P, F);
 	// U = weight*(J-1)*(J-1) with weight == 1: (1*(J-1))*(J-1) == (J-1)^2
 	float U = VolumetricFromF<EXACT>(e, F, 1.0f, g);
-	ConstrainOne<EXACT, false>(sc, p, e.idx, v, U, g, comp, 0.0f);
+	ConstrainOne<EXACT, false>(vs, p, e.idx, v, U, g, comp, 0.0f);
 #pragma unroll
-	for (int n = 0; n < 4; n++) { StoreVertex(sc.Xw, is[n], v[n]); }
+	for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
 }
 
 // DampElement: SolveElementMixed in DampingMode::On, Fem.cpp:910-929, 555-563; RayleighDamp Xpbd.h:216-263.
-template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void DampElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& e) {
+template <int ENERGY, bool SIMUL, bool EXACT, typename VS, typename PARAMS>
+__device__ __forceinline__ void DampElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
 	VertexRegs v[4];
@@ -473,8 +505,8 @@ __device__ __forceinline__ void DampElement(const DeviceScene& sc, const Substep
 	float fv[4][3];
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
-		v[n] = LoadVertex(sc.Xw, is[n]);
-		LoadD3(sc.V, is[n], vel[n]);
+		v[n] = vs.LoadX(is[n]);
+		vs.LoadV(is[n], vel[n]);
 #pragma unroll
 		for (int k = 0; k < 3; k++) { fv[n][k] = __double2float_rn(vel[n][k]); }
 	}
@@ -537,7 +569,7 @@ __device__ __forceinline__ void DampElement(const DeviceScene& sc, const Substep
 		}
 	}
 #pragma unroll
-	for (int n = 0; n < 4; n++) { StoreD3(sc.V, is[n], vel[n]); }
+	for (int n = 0; n < 4; n++) { vs.StoreV(is[n], vel[n]); }
 }
 
 // inverse(mat3) with fp64 cofactors, vectormath.cpp:41-60 (PbdDamp's inertia tensor).
@@ -570,15 +602,15 @@ __device__ __forceinline__ void InverseViaDouble(const float (&m)[3][3], float (
 }
 
 // PbdDamp<4>, Xpbd.h:309-348
-template <bool EXACT>
-__device__ __forceinline__ void PbdDampElement(const DeviceScene& sc, const SubstepParams& p, uint32_t e, const uint4& idx) {
+template <bool EXACT, typename VS, typename PARAMS>
+__device__ __forceinline__ void PbdDampElement(const VS& vs, const PARAMS& p, float surfaceArea, const uint4& idx) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { idx.x, idx.y, idx.z, idx.w };
-	float damping = fminf(1.0f, O::div(p.pbdDamping, __ldg(sc.eArea + e)));
+	float damping = fminf(1.0f, O::div(p.pbdDamping, surfaceArea));
 	VertexRegs v[4];
 	double vel[4][3];
 #pragma unroll
-	for (int n = 0; n < 4; n++) { v[n] = LoadVertex(sc.Xw, is[n]); LoadD3(sc.V, is[n], vel[n]); }
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); vs.LoadV(is[n], vel[n]); }
 	float X[4][3], Vf[4][3], M[4];
 	float Wsum = 1.0e-8f;
 #pragma unroll
@@ -637,7 +669,7 @@ __device__ __forceinline__ void PbdDampElement(const DeviceScene& sc, const Subs
 			float dV = O::sub(O::add(Vcm[k], cr[k]), Vf[n][k]);
 			vel[n][k] = O::dadd(vel[n][k], (double)O::mul(damping, dV));
 		}
-		StoreD3(sc.V, is[n], vel[n]);
+		vs.StoreV(is[n], vel[n]);
 	}
 }
 

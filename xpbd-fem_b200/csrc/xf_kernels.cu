@@ -6,6 +6,7 @@
 #include <cooperative_groups.h>
 
 #include "xf_element.cuh"
+#include "xf_dispatch.cuh"
 
 namespace xf {
 
@@ -105,10 +106,11 @@ __device__ __forceinline__ void SweepLoad(const DeviceScene& sc, uint32_t e, Ele
 }
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 __device__ __forceinline__ void SweepRun(const DeviceScene& sc, const SubstepParams& p, uint32_t e, const ElemRec& rec) {
-	if (KIND == 0) { SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(sc, p, rec); }
-	if (KIND == 1) { SolveVolumeOnly<EXACT>(sc, p, rec); }
-	if (KIND == 2) { DampElement<ENERGY, SIMUL, EXACT>(sc, p, rec); }
-	if (KIND == 3) { PbdDampElement<EXACT>(sc, p, e, rec.idx); }
+	const GlobalStore vs = StoreOf(sc);
+	if (KIND == 0) { SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec); }
+	if (KIND == 1) { SolveVolumeOnly<EXACT>(vs, p, rec); }
+	if (KIND == 2) { DampElement<ENERGY, SIMUL, EXACT>(vs, p, rec); }
+	if (KIND == 3) { PbdDampElement<EXACT>(vs, p, __ldg(sc.eArea + e), rec.idx); }
 }
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 __device__ __forceinline__ void SweepOne(const DeviceScene& sc, const SubstepParams& p, uint32_t e) {
@@ -364,27 +366,6 @@ cudaError_t LaunchSweepT(const DeviceScene& sc, const SubstepParams& p, uint32_t
 	if (b >= e) { return cudaSuccess; }
 	k_sweep_color<KIND, ENERGY, SIMUL, EXACT, DAMPED><<<GridFor(e - b, 256), 256, 0, st>>>(sc, p, b, e);
 	return cudaGetLastError();
-}
-
-// Runtime (energy, simultaneous, exact, damped) -> template instantiation.
-template <template <int, bool, bool, bool> class Fn, typename... Args>
-cudaError_t DispatchConfig(uint32_t energy, bool simul, bool exact, bool damped, Args&&... args) {
-#define XF_CASE(E)                                                                                                      \
-	case E:                                                                                                             \
-		if (simul) {                                                                                                    \
-			if (exact) { return damped ? Fn<E, true, true, true>::Run(args...) : Fn<E, true, true, false>::Run(args...); } \
-			return damped ? Fn<E, true, false, true>::Run(args...) : Fn<E, true, false, false>::Run(args...);           \
-		}                                                                                                               \
-		if (exact) { return damped ? Fn<E, false, true, true>::Run(args...) : Fn<E, false, true, false>::Run(args...); } \
-		return damped ? Fn<E, false, false, true>::Run(args...) : Fn<E, false, false, false>::Run(args...);
-	switch (energy) {
-		XF_CASE(XF_ENERGY_MIXED)
-		XF_CASE(XF_ENERGY_MIXED_SEL)
-		XF_CASE(XF_ENERGY_YEOH_SKIN)
-		XF_CASE(XF_ENERGY_YEOH_SKIN_FAST)
-	default: return cudaErrorInvalidValue;
-	}
-#undef XF_CASE
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>

@@ -89,6 +89,28 @@ struct SubstepParams {
 	uint32_t nColors;
 };
 
+// Per-scene constants of a batched call (xf_batch.cu): the scalar part of SubstepParams.  The element math is
+// templated on the parameter type and only touches fields that exist in both.
+struct SceneConsts {
+	float dt, dt2, invDt;
+	float gdtX, gdtY;
+	float keep;
+	float invMu, invLambda, a;
+	float damping;
+	float compliance;
+	float pbdDamping;
+	float dampDamping;
+	uint32_t rayleigh;
+	uint32_t lockLeft, lockRight;
+	uint32_t volumePasses;
+	uint32_t tickId;
+	uint32_t doDamp, doPbdDamp;
+	float lockT[12];
+	float origin[3];
+	uint32_t groundOn;
+	float groundY, groundKeep;
+};
+
 struct LaunchShape {
 	int blockThreads = 256;
 	int gridBlocks = 0;     // persistent grid (co-resident)
@@ -114,6 +136,10 @@ int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* i
                 bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err);
 int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
                       std::string* err);
+
+// error reporting shared by the ABI translation units (xf_api.cpp)
+int Fail(int status, const std::string& msg);
+int FailCuda(cudaError_t e, const char* what);
 
 // ---- kernel launchers (xf_kernels.cu) ----
 cudaError_t QueryLaunchShape(int device, uint32_t energy, bool exact, LaunchShape* shape);
