@@ -420,3 +420,70 @@ class OracleScene:
 
     def time_substeps(self, settings, dt, n):
         return float(self.lib.xo_time_substeps(self.h, C.byref(settings), dt, n))
+
+
+# ---------------------------------------------------------------------------------------------
+# The product's reference-side adapter (GeoLinear3dCuda : Geo) hosted by the reference harness
+# ---------------------------------------------------------------------------------------------
+class AdapterScene:
+    """oracle/_ref/libxpbd_ref_adapter.so: the reference's `Geo` virtual interface, implemented by the CUDA library."""
+
+    def __init__(self, nodes, idx_stream, density=1.0, auto_resize=False, color_hint=None):
+        lib = C.CDLL(ref_lib_path("adapter"))
+        vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
+        lib.ref_adapter_create.restype = vp
+        lib.ref_adapter_create.argtypes = [vp, u32, vp, u32, f32, C.c_int, vp]
+        lib.ref_adapter_destroy.argtypes = [vp]
+        lib.ref_adapter_vert_count.restype = u32
+        lib.ref_adapter_vert_count.argtypes = [vp]
+        lib.ref_adapter_element_count.restype = u32
+        lib.ref_adapter_element_count.argtypes = [vp]
+        lib.ref_adapter_get_order.argtypes = [vp, vp]
+        lib.ref_adapter_substep.argtypes = [vp, vp, vp, f32, u32]
+        lib.ref_adapter_volume.restype = f32
+        lib.ref_adapter_volume.argtypes = [vp]
+        lib.ref_adapter_transform.argtypes = [vp, vp]
+        lib.ref_adapter_get_state.argtypes = [vp, vp, vp, vp]
+        self.lib = lib
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        hint = None if color_hint is None else np.ascontiguousarray(color_hint, dtype=np.uint32)
+        h = lib.ref_adapter_create(_vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, density, 1 if auto_resize else 0, _vp(hint))
+        if not h:
+            raise RuntimeError("GeoLinear3dCuda::Init failed (no CUDA device?)")
+        self.h = C.c_void_p(h)
+        self.nV = lib.ref_adapter_vert_count(self.h)
+        self.nT = lib.ref_adapter_element_count(self.h)
+
+    def close(self):
+        if self.h:
+            self.lib.ref_adapter_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def get_order(self):
+        o = np.empty(self.nT, dtype=np.uint32)
+        self.lib.ref_adapter_get_order(self.h, _vp(o))
+        return o
+
+    def substep(self, settings, dt, n=1, manip=None):
+        self.lib.ref_adapter_substep(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, dt, n)
+
+    def volume(self):
+        return float(self.lib.ref_adapter_volume(self.h))
+
+    def transform(self, m9):
+        m9 = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)
+        self.lib.ref_adapter_transform(self.h, _vp(m9))
+
+    def get_state(self):
+        X = np.empty((self.nV, 3), dtype=np.float64)
+        V = np.empty((self.nV, 3), dtype=np.float64)
+        w = np.empty(self.nV, dtype=np.float32)
+        self.lib.ref_adapter_get_state(self.h, _vp(X), _vp(V), _vp(w))
+        return X, V, w

@@ -309,6 +309,53 @@ void ref_substep_ext(void* h, const void* settings160, const void* manipPod, flo
 	}
 }
 
+#ifdef XF_WITH_CUDA_ADAPTER
+}  // extern "C"
+// ---- drop-in demonstration: the product's reference-side adapter driven through the reference's own `Geo`
+// virtual interface, exactly like Sim::Update does (Demo.cpp:86-88). Built only into libxpbd_ref_adapter.so. ----
+#include "GeoLinear3dCuda.h"
+extern "C" {
+struct AdapterScene {
+	Geo* geo = nullptr;            // virtual calls only
+	GeoLinear3dCuda* impl = nullptr;
+};
+void* ref_adapter_create(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density, int autoResize,
+                         const uint32_t* colorHint) {
+	AdapterScene* a = new AdapterScene();
+	a->impl = new GeoLinear3dCuda();
+	if (!a->impl->Init(density, nodeXYZ, nodeFloatCount, idxStream, idxCount, autoResize != 0, 0, XF_PRECISION_EXACT, colorHint)) {
+		delete a->impl; delete a; return nullptr;
+	}
+	a->geo = a->impl;
+	a->geo->volume0 = a->geo->CalculateVolume();
+	return a;
+}
+void ref_adapter_destroy(void* h) { AdapterScene* a = (AdapterScene*)h; if (a) { delete a->impl; delete a; } }
+uint32_t ref_adapter_vert_count(void* h) { return ((AdapterScene*)h)->geo->VertCount(); }
+uint32_t ref_adapter_element_count(void* h) { return ((AdapterScene*)h)->geo->ElementCount(); }
+void ref_adapter_get_order(void* h, uint32_t* order) { xf_get_order(((AdapterScene*)h)->impl->scene, order); }
+void ref_adapter_substep(void* h, const void* settings160, const void* manipPod, float dt, uint32_t n) {
+	AdapterScene* a = (AdapterScene*)h;
+	Settings settings;
+	memcpy((void*)&settings, settings160, sizeof(Settings));
+	Manipulator manip = ToManip((const ManipPod*)manipPod, a->geo);
+	for (uint32_t k = 0; k < n; k++) {
+		a->geo->Substep(settings, manip, dt); // virtual dispatch, one substep per call like the reference
+		settings.tickId++;
+	}
+}
+float ref_adapter_volume(void* h) { return ((AdapterScene*)h)->geo->CalculateVolume(); }
+void ref_adapter_transform(void* h, const float* m9) { ((AdapterScene*)h)->geo->Transform(mat3(V3(m9 + 0), V3(m9 + 3), V3(m9 + 6))); }
+void ref_adapter_get_state(void* h, double* X, double* V, float* w) {
+	AdapterScene* a = (AdapterScene*)h;
+	a->impl->RefreshMirror();
+	const size_t n = a->impl->hostW.size();
+	if (X) { memcpy(X, a->impl->hostX.data(), sizeof(double) * 3 * n); }
+	if (V) { memcpy(V, a->impl->hostV.data(), sizeof(double) * 3 * n); }
+	if (w) { memcpy(w, a->impl->hostW.data(), sizeof(float) * n); }
+}
+#endif
+
 // Timing leg for bench.py: run `n` reference substeps and return elapsed seconds.
 double ref_time_substeps(void* h, const void* settings160, float dt, uint32_t n) {
 	auto t0 = std::chrono::steady_clock::now();

@@ -1,0 +1,100 @@
+// Reference-side adapter: a `Geo` (Geo.h:15-35) whose Substep runs on the B200 through the C ABI.
+//
+// Compile this header INSIDE the reference tree (it includes the reference's Geo.h); it is not part of
+// libxpbd_fem_b200.so.  `Sim` only talks to `Geo*` through virtuals (Demo.cpp:86-88, 105-113, 156-162), so
+// constructing a GeoLinear3dCuda instead of a GeoLinear3d in Sim::AddBlock (Demo.cpp:140-144) is the whole
+// integration.  Geo3d::Substep is `final` (Geo.h:56), hence the adapter derives from Geo, not Geo3d.
+//
+// oracle/ref_harness.cpp builds this adapter against the unmodified reference headers
+// (oracle/_ref/libxpbd_ref_adapter.so) and tests/test_gpu_adapter.py drives both Geo implementations
+// through the same virtual calls.
+#pragma once
+
+#include <float.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "Geo.h"
+#include "xpbd_fem_b200.h"
+
+struct GeoLinear3dCuda : public Geo {
+	xf_scene* scene = nullptr;
+	std::vector<double> hostX, hostV; // lazily refreshed mirror for Pick/Render
+	std::vector<float> hostW;
+	std::vector<uint8_t> hostFlags;
+	bool mirrorValid = false;
+
+	// Same signature as GeoLinear3d::Init (Geo.h:147) minus the Allocator: device memory is owned by the library.
+	bool Init(float density, const float* nodeData, uint32_t nodeDataCount, const uint32_t* idxData, uint32_t idxDataCount, bool autoResize,
+	          int device = 0, int precision = XF_PRECISION_EXACT, const uint32_t* colorHint = nullptr) {
+		xf_create_params p;
+		xf_default_create_params(&p);
+		p.device = device;
+		p.density = density;
+		p.autoResize = autoResize ? 1 : 0;
+		p.precision = precision;
+		p.colorHint = colorHint;
+		p.colorHintCount = colorHint ? idxDataCount / 5 : 0;
+		if (xf_create(&p, nodeData, nodeDataCount, idxData, idxDataCount, &scene) != XF_OK) {
+			fprintf(stderr, "GeoLinear3dCuda::Init: %s\n", xf_last_error());
+			return false;
+		}
+		hostFlags.resize(xf_vert_count(scene));
+		xf_get_rest(scene, nullptr, nullptr, hostFlags.data());
+		return true;
+	}
+	~GeoLinear3dCuda() { xf_destroy(scene); }
+
+	void Substep(const Settings& settings, const Manipulator& manip, float dt) final {
+		static_assert(sizeof(Settings) == sizeof(xf_settings), "Settings POD must stay byte-identical to xf_settings");
+		xf_manipulator m;
+		memcpy(m.pos, &manip.pos, 12); memcpy(m.manipPlaneNormal, &manip.manipPlaneNormal, 12); memcpy(m.pick0, &manip.pick0, 12);
+		memcpy(m.pickDir, &manip.pickDir, 12); memcpy(m.pickDirOld, &manip.pickDirOld, 12); memcpy(m.pickDirTarget, &manip.pickDirTarget, 12);
+		m.picked = manip.pickedGeo == this ? 1 : 0; // Geo.cpp:334
+		m.pickedPointIdx = manip.pickedPointIdx;
+		if (xf_substep(scene, reinterpret_cast<const xf_settings*>(&settings), &m, dt, 1) != XF_OK) {
+			fprintf(stderr, "GeoLinear3dCuda::Substep: %s\n", xf_last_error());
+		}
+		mirrorValid = false;
+	}
+	void Transform(mat3 t) final {
+		const float m9[9] = { t[0][0], t[0][1], t[0][2], t[1][0], t[1][1], t[1][2], t[2][0], t[2][1], t[2][2] };
+		xf_transform(scene, m9);
+		mirrorValid = false;
+	}
+	// Constrain/Damp are sub-phases of Substep in the reference; on the device they are fused into xf_substep.
+	void Constrain(const Settings&, float) final {}
+	void Damp(const Settings&, float) final {}
+	float CalculateVolume() const final {
+		float v = 0.0f;
+		xf_volume(scene, &v);
+		return v;
+	}
+	uint32_t VertCount() const final { return xf_vert_count(scene); }
+	uint32_t ElementCount() const final { return xf_element_count(scene); }
+
+	void RefreshMirror() {
+		if (mirrorValid) { return; }
+		const uint32_t n = xf_vert_count(scene);
+		hostX.resize(3 * (size_t)n); hostV.resize(3 * (size_t)n); hostW.resize(n);
+		xf_get_state(scene, hostX.data(), hostV.data(), hostW.data());
+		mirrorValid = true;
+	}
+	// UI helpers (out of the hot-path scope): nearest pickable vertex to the ray, from the host mirror.
+	void Pick(vec3 rayOrigin, vec3 rayDir, vec3* outNearestPoint, uint32_t* outNearestPointIdx, float* outDistance) final {
+		RefreshMirror();
+		float best = FLT_MAX;
+		for (uint32_t i = 0; i < hostFlags.size(); i++) {
+			if (!(hostFlags[i] & Geo::Pickable)) { continue; }
+			vec3 p = vec3((float)hostX[3 * i], (float)hostX[3 * i + 1], (float)hostX[3 * i + 2]);
+			float t = dot(rayDir, p - rayOrigin);
+			if (t < 0.0f) { continue; }
+			float d = distance(p, rayOrigin + t * rayDir);
+			if (d < best) { best = d; *outNearestPoint = p; *outNearestPointIdx = i; }
+		}
+		*outDistance = best;
+	}
+	void Render(const Settings&) final { RefreshMirror(); /* draw from hostX with the host's renderer */ }
+};
