@@ -5,9 +5,8 @@
 // constructing a GeoLinear3dCuda instead of a GeoLinear3d in Sim::AddBlock (Demo.cpp:140-144) is the whole
 // integration.  Geo3d::Substep is `final` (Geo.h:56), hence the adapter derives from Geo, not Geo3d.
 //
-// oracle/ref_harness.cpp builds this adapter against the unmodified reference headers
-// (oracle/_ref/libxpbd_ref_adapter.so) and tests/test_gpu_adapter.py drives both Geo implementations
-// through the same virtual calls.
+// The test harness builds this adapter against the unmodified reference headers and
+// tests/test_gpu_adapter.py drives both Geo implementations through the same virtual calls.
 #pragma once
 
 #include <float.h>
