@@ -217,6 +217,42 @@ int xf_batch_get_state(xf_batch* batch, uint32_t firstScene, uint32_t count, dou
 int xf_batch_set_state(xf_batch* batch, uint32_t firstScene, uint32_t count, const double* X, const double* V, const float* w);
 int xf_batch_get_info(const xf_batch* batch, uint32_t* groupThreads, uint32_t* blockThreads, uint32_t* smemBytes, uint64_t* launches);
 
+/* ---- one mesh on several GPUs (BASELINE config 4) ----
+ * Every rank (one process per GPU) calls xf_part_create with the SAME full mesh and its own rank; the library
+ * computes the same partition plan everywhere (x-slabs of elements, local copies of the touched vertices, global
+ * colouring).  The per-colour halo exchange is fused into the sweep kernels as stores into the peers' vertex
+ * arrays over NVLink (CUDA IPC mappings) plus flag signalling; the host only has to move each rank's 128-byte
+ * xf_part_ipc_export blob to all ranks once (torch.distributed / MPI / files) and hand them to
+ * xf_part_ipc_connect.  All ranks must then issue the same xf_part_substep calls.  Results equal the
+ * single-GPU schedule bit for bit.  device < 0 creates a host-only plan (no stepping) whose halo lists can be
+ * inspected; damping sweeps and volume passes are not implemented on this path (XF_ERR_UNSUPPORTED). */
+typedef struct xf_partition xf_partition;
+#define XF_IPC_BYTES 128
+int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream,
+                   uint32_t idxCount, uint32_t nRanks, uint32_t rank, xf_partition** outPart);
+int xf_part_destroy(xf_partition* part);
+uint32_t xf_part_local_vert_count(const xf_partition* part);
+uint32_t xf_part_local_element_count(const xf_partition* part);
+uint32_t xf_part_peer_count(const xf_partition* part);
+uint32_t xf_part_color_count(const xf_partition* part);
+uint32_t xf_part_global_vert_count(const xf_partition* part);
+uint32_t xf_part_global_element_count(const xf_partition* part);
+int xf_part_get_local_verts(const xf_partition* part, uint32_t* localToGlobal);
+int xf_part_get_local_elements(const xf_partition* part, uint32_t* globalElementIds, uint32_t* colorStart /* colours + 1 */);
+int xf_part_get_peers(const xf_partition* part, uint32_t* peerRanks);
+/* vertices (local ids, ascending global id) sent to / received from peer `peerSlot` after colour `color` */
+int xf_part_get_halo(const xf_partition* part, uint32_t color, uint32_t peerSlot, int send, uint32_t* count, uint32_t* localVerts);
+int xf_part_get_order(const xf_partition* part, uint32_t* fullOrder);
+int xf_part_get_global_color_start(const xf_partition* part, uint32_t* colorStart);
+int xf_part_get_initial(const xf_partition* part, float* w, uint8_t* flags);
+int xf_part_ipc_export(xf_partition* part, void* out128);
+int xf_part_ipc_connect(xf_partition* part, const void* allRanksBlobs);
+int xf_part_set_ground(xf_partition* part, int enabled, float y0, float friction);
+int xf_part_substep(xf_partition* part, const xf_settings* settings, float dt, uint32_t n);
+int xf_part_sync(xf_partition* part);
+int xf_part_get_state(xf_partition* part, double* X, double* V, float* w); /* local vertices */
+int xf_part_get_info(const xf_partition* part, uint64_t* launches, uint64_t* epoch);
+
 #ifdef __cplusplus
 }
 #endif

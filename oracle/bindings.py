@@ -299,6 +299,10 @@ def _load_oracle():
     lib.xo_get_origin.argtypes = [vp, vp]
     lib.xo_substep.argtypes = [vp, vp, vp, f32, u32]
     lib.xo_set_ground.argtypes = [vp, C.c_int, f32, f32]
+    lib.xo_phase_predict.argtypes = [vp, vp, f32]
+    lib.xo_phase_sweep.argtypes = [vp, vp, f32, u32, u32]
+    lib.xo_phase_post.argtypes = [vp, vp, vp, f32]
+    lib.xo_set_flags.argtypes = [vp, vp]
     lib.xo_set_handles.argtypes = [vp, u32, vp, vp]
     lib.xo_transform.argtypes = [vp, vp]
     lib.xo_volume.restype = f32
@@ -409,6 +413,20 @@ class OracleScene:
 
     def substep(self, settings, dt, n=1, manip=None, ext=False):
         self.lib.xo_substep(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, dt, n)
+
+    def phase_predict(self, settings, dt):
+        self.lib.xo_phase_predict(self.h, C.byref(settings), dt)
+
+    def phase_sweep(self, settings, dt, begin, end):
+        self.lib.xo_phase_sweep(self.h, C.byref(settings), dt, begin, end)
+
+    def phase_post(self, settings, dt, manip=None):
+        self.lib.xo_phase_post(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, dt)
+
+    def set_flags(self, flags):
+        flags = np.ascontiguousarray(flags, dtype=np.uint8)
+        assert flags.size == self.nV
+        self.lib.xo_set_flags(self.h, _vp(flags))
 
     def set_ground(self, enabled, y0=0.0, friction=0.0):
         self.lib.xo_set_ground(self.h, 1 if enabled else 0, y0, friction)

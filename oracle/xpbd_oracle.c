@@ -334,6 +334,7 @@ void xo_get_elements(const xo_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, 
 		if (area) { area[e] = t->surfaceArea; }
 	}
 }
+void xo_set_flags(xo_scene* s, const uint8_t* flags) { memcpy(s->flags, flags, s->nV); }
 void xo_get_origin(const xo_scene* s, float* o) { o[0] = s->origin[0]; o[1] = s->origin[1]; o[2] = s->origin[2]; }
 
 /* ------------------------------------------------------------------------------------------
@@ -771,74 +772,87 @@ static void drag_vertex(xo_scene* s, uint32_t i, const float* target, float dt) 
 	}
 }
 
+/* ---- Geo3d::Substep, Geo.cpp:305-356, in three phases so tests can emulate a partitioned run ---- */
+/* predict, Geo.cpp:307-312 */
+void xo_phase_predict(xo_scene* s, const xo_settings* st, float dt) {
+	double gdt[3] = { (double)(st->gravity[0] * dt), (double)(st->gravity[1] * dt), (double)0.0f };
+	double keep = (double)(1.0f - st->timeCorrectedDrag);
+	double ddt = (double)dt;
+	for (uint32_t i = 0; i < s->nV; i++) {
+		for (int k = 0; k < 3; k++) {
+			size_t q = 3 * (size_t)i + k;
+			s->V[q] = s->V[q] + gdt[k];
+			s->V[q] = s->V[q] * keep;
+			s->O[q] = s->X[q];
+			s->X[q] = s->X[q] + s->V[q] * ddt;
+		}
+	}
+}
+
+/* elements tOrder[begin..end) of the main sweep of GeoLinear3d::Constrain, Geo.cpp:777 */
+void xo_phase_sweep(xo_scene* s, const xo_settings* st, float dt, uint32_t begin, uint32_t end) {
+	uint32_t energy = (st->flags >> XO_ENERGY_BIT) & XO_ENERGY_MASK;
+	if (!energy_supported(energy)) { energy = EN_MIXED_SEL; }
+	for (uint32_t i = begin; i < end && i < s->nT; i++) { solve_element_mixed(energy, 0, dt, s->X, s->O, NULL, s->w, &s->t[s->tOrder[i]], st); }
+}
+
+/* ground (x1) -> locks -> manipulator -> handles (x2) -> velocity update, Geo.cpp:318-344 */
+void xo_phase_post(xo_scene* s, const xo_settings* stp, const xo_manipulator* manip, float dt) {
+	const xo_settings st = *stp;
+	if (s->groundOn) {
+		double y0 = (double)s->groundY;
+		double keepT = (double)(1.0f - s->groundFriction);
+		for (uint32_t i = 0; i < s->nV; i++) {
+			size_t q = 3 * (size_t)i;
+			if (s->X[q + 1] < y0) {
+				s->X[q + 1] = y0;
+				s->X[q + 0] = s->O[q + 0] + (s->X[q + 0] - s->O[q + 0]) * keepT;
+				s->X[q + 2] = s->O[q + 2] + (s->X[q + 2] - s->O[q + 2]) * keepT;
+			}
+		}
+	}
+	if (st.flags & XO_LOCK_LEFT) {
+		for (uint32_t i = 0; i < s->nV; i++) {
+			if (s->flags[i] & XO_FLAG_LEFT) { for (int k = 0; k < 3; k++) { s->X[3 * (size_t)i + k] = s->O[3 * (size_t)i + k]; } s->w[i] = 0.0f; }
+		}
+	}
+	if (st.flags & XO_LOCK_RIGHT) {
+		for (uint32_t i = 0; i < s->nV; i++) {
+			if (s->flags[i] & XO_FLAG_RIGHT) {
+				float x0[3] = { (float)s->X0[3 * (size_t)i], (float)s->X0[3 * (size_t)i + 1], (float)s->X0[3 * (size_t)i + 2] };
+				for (int r = 0; r < 3; r++) {
+					/* mat3 * vec3 with 16-byte padded columns */
+					float v = st.lockedRightTransform3d[0 + r] * x0[0] + st.lockedRightTransform3d[4 + r] * x0[1] + st.lockedRightTransform3d[8 + r] * x0[2];
+					double p = (double)(s->origin[r] + v);
+					s->X[3 * (size_t)i + r] = p;
+					s->O[3 * (size_t)i + r] = p;
+				}
+				s->w[i] = 0.0f;
+			}
+		}
+	}
+	if (manip && manip->picked) {
+		const float* nrm = manip->manipPlaneNormal;
+		float d[3] = { manip->pick0[0] - manip->pos[0], manip->pick0[1] - manip->pos[1], manip->pick0[2] - manip->pos[2] };
+		float t = dot3(nrm, d) / dot3(nrm, manip->pickDirTarget);
+		float target[3];
+		for (int c = 0; c < 3; c++) { target[c] = manip->pos[c] + t * manip->pickDirTarget[c]; }
+		drag_vertex(s, manip->pickedPointIdx, target, dt);
+	}
+	for (uint32_t hd = 0; hd < s->handleCount; hd++) { drag_vertex(s, s->handleIdx[hd], s->handleTarget[hd], dt); }
+	double invDt = (double)(1.0f / dt);
+	for (uint32_t i = 0; i < s->nV; i++) {
+		for (int k = 0; k < 3; k++) { size_t q = 3 * (size_t)i + k; s->V[q] = (s->X[q] - s->O[q]) * invDt; }
+	}
+}
+
 /* Geo3d::Substep, Geo.cpp:305-356 */
 void xo_substep(xo_scene* s, const xo_settings* settingsIn, const xo_manipulator* manip, float dt, uint32_t n) {
 	xo_settings st = *settingsIn;
 	for (uint32_t step = 0; step < n; step++) {
-		/* predict, Geo.cpp:307-312 */
-		double gdt[3] = { (double)(st.gravity[0] * dt), (double)(st.gravity[1] * dt), (double)0.0f };
-		double keep = (double)(1.0f - st.timeCorrectedDrag);
-		double ddt = (double)dt;
-		for (uint32_t i = 0; i < s->nV; i++) {
-			for (int k = 0; k < 3; k++) {
-				size_t q = 3 * (size_t)i + k;
-				s->V[q] = s->V[q] + gdt[k];
-				s->V[q] = s->V[q] * keep;
-				s->O[q] = s->X[q];
-				s->X[q] = s->X[q] + s->V[q] * ddt;
-			}
-		}
+		xo_phase_predict(s, &st, dt);
 		constrain(s, &st, dt);
-		/* extension x1: ground plane; after Constrain, before the locks */
-		if (s->groundOn) {
-			double y0 = (double)s->groundY;
-			double keepT = (double)(1.0f - s->groundFriction);
-			for (uint32_t i = 0; i < s->nV; i++) {
-				size_t q = 3 * (size_t)i;
-				if (s->X[q + 1] < y0) {
-					s->X[q + 1] = y0;
-					s->X[q + 0] = s->O[q + 0] + (s->X[q + 0] - s->O[q + 0]) * keepT;
-					s->X[q + 2] = s->O[q + 2] + (s->X[q + 2] - s->O[q + 2]) * keepT;
-				}
-			}
-		}
-		/* locks, Geo.cpp:318-331 */
-		if (st.flags & XO_LOCK_LEFT) {
-			for (uint32_t i = 0; i < s->nV; i++) {
-				if (s->flags[i] & XO_FLAG_LEFT) { for (int k = 0; k < 3; k++) { s->X[3 * (size_t)i + k] = s->O[3 * (size_t)i + k]; } s->w[i] = 0.0f; }
-			}
-		}
-		if (st.flags & XO_LOCK_RIGHT) {
-			for (uint32_t i = 0; i < s->nV; i++) {
-				if (s->flags[i] & XO_FLAG_RIGHT) {
-					float x0[3] = { (float)s->X0[3 * (size_t)i], (float)s->X0[3 * (size_t)i + 1], (float)s->X0[3 * (size_t)i + 2] };
-					for (int r = 0; r < 3; r++) {
-						/* mat3 * vec3 with 16-byte padded columns */
-						float v = st.lockedRightTransform3d[0 + r] * x0[0] + st.lockedRightTransform3d[4 + r] * x0[1] + st.lockedRightTransform3d[8 + r] * x0[2];
-						double p = (double)(s->origin[r] + v);
-						s->X[3 * (size_t)i + r] = p;
-						s->O[3 * (size_t)i + r] = p;
-					}
-					s->w[i] = 0.0f;
-				}
-			}
-		}
-		/* manipulator, Geo.cpp:333-339 */
-		if (manip && manip->picked) {
-			const float* nrm = manip->manipPlaneNormal;
-			float d[3] = { manip->pick0[0] - manip->pos[0], manip->pick0[1] - manip->pos[1], manip->pick0[2] - manip->pos[2] };
-			float t = dot3(nrm, d) / dot3(nrm, manip->pickDirTarget);
-			float target[3];
-			for (int c = 0; c < 3; c++) { target[c] = manip->pos[c] + t * manip->pickDirTarget[c]; }
-			drag_vertex(s, manip->pickedPointIdx, target, dt);
-		}
-		/* extension x2: additional drag handles, same projection per handle */
-		for (uint32_t hd = 0; hd < s->handleCount; hd++) { drag_vertex(s, s->handleIdx[hd], s->handleTarget[hd], dt); }
-		/* velocity update, Geo.cpp:342-344 */
-		double invDt = (double)(1.0f / dt);
-		for (uint32_t i = 0; i < s->nV; i++) {
-			for (int k = 0; k < 3; k++) { size_t q = 3 * (size_t)i + k; s->V[q] = (s->X[q] - s->O[q]) * invDt; }
-		}
+		xo_phase_post(s, &st, manip, dt);
 		/* damping, Geo.cpp:346-355 */
 		uint32_t rayleighType = (st.flags >> XO_RAYLEIGH_BIT) & XO_RAYLEIGH_MASK;
 		if (rayleighType == RAY_POST_AMORTIZED) {

@@ -57,6 +57,12 @@ void xo_get_origin(const xo_scene* s, float* o);
 
 /* Geo3d::Substep, Geo.cpp:305-356 (+ ground / handles extensions). */
 void xo_substep(xo_scene* s, const xo_settings* settings, const xo_manipulator* manip, float dt, uint32_t n);
+/* The same substep split into phases (predict | sweep of tOrder[begin,end) | post); used by the tests that emulate a
+ * partitioned multi-rank run on CPU. */
+void xo_phase_predict(xo_scene* s, const xo_settings* settings, float dt);
+void xo_phase_sweep(xo_scene* s, const xo_settings* settings, float dt, uint32_t begin, uint32_t end);
+void xo_phase_post(xo_scene* s, const xo_settings* settings, const xo_manipulator* manip, float dt);
+void xo_set_flags(xo_scene* s, const uint8_t* flags);
 void xo_set_ground(xo_scene* s, int enabled, float y0, float friction);
 void xo_set_handles(xo_scene* s, uint32_t count, const uint32_t* vertIdx, const float* targetXYZ);
 

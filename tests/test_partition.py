@@ -1,0 +1,95 @@
+"""Single-mesh multi-rank path.
+
+CPU (gloo, world_size 2 and 3): the partition plan (slabs, local vertex copies, per-colour halo send/recv lists)
+is exercised by EMULATING the partitioned algorithm - C oracle as the element solver, gloo send/recv as the
+transport - and comparing with the unpartitioned oracle: bit-exact.  This covers all the host logic of the N > 1
+path without a GPU.
+
+GPU (needs >= 2 devices; skipped otherwise): the library itself, in-kernel peer stores over NVLink, vs the oracle."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from __graft_entry__ import ROOT, build, load_package
+
+build()
+xf = load_package()
+WORKER = os.path.join(ROOT, "tools", "part_worker.py")
+
+
+def run_ranks(world, args, port, timeout=600):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(port), WORKER] + args
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    lines = [l for l in p.stdout.splitlines() if l.startswith("PART_RESULT ")]
+    assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
+    return json.loads(lines[-1][len("PART_RESULT "):])
+
+
+def test_plan_is_consistent_across_ranks():
+    nodes, idx, hint = xf.GenerateTetBlock(8, 3, wonkiness=0.1)
+    world = 3
+    parts = [xf.GeoPartitionCuda(nodes, idx, world, r, device=-1, color_hint=hint) for r in range(world)]
+    tets = idx.reshape(-1, 5)[:, 1:]
+    # every element owned exactly once; local vertex sets cover exactly the touched vertices
+    owned = np.concatenate([p.local_elements()[0] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(len(tets)))
+    for p in parts:
+        e, cs = p.local_elements()
+        assert np.array_equal(np.unique(tets[e]), p.local_verts())
+        assert cs[0] == 0 and cs[-1] == p.nT and np.all(np.diff(cs.astype(np.int64)) >= 0)
+    # send list of r towards q == recv list of q from r, as GLOBAL vertex ids, colour by colour
+    for r in range(world):
+        for slot, q in enumerate(parts[r].peers()):
+            back = list(parts[q].peers()).index(r)
+            for c in range(parts[r].nColors):
+                snd = parts[r].local_verts()[parts[r].halo(c, slot, True)]
+                rcv = parts[q].local_verts()[parts[q].halo(c, back, False)]
+                assert np.array_equal(snd, rcv)
+    # slabs: only neighbouring ranks share vertices
+    assert list(parts[0].peers()) == [1] and list(parts[1].peers()) == [0, 2] and list(parts[2].peers()) == [1]
+
+
+@pytest.mark.parametrize("world,extra", [(2, []), (3, ["--energy", "4", "--poisson", "0.495"]), (2, ["--serial", "--energy", "3", "--no-hint"]),
+                                         (2, ["--pattern", "1", "--energy", "5"])])
+def test_partitioned_emulation_matches_single_scene_oracle(world, extra):
+    out = run_ranks(world, ["--mode", "emulate", "--dims", "8", "3", "--substeps", "6"] + extra, 29611 + world)
+    assert out["ok"], out["msg"]
+    assert out["shared_verts_rank0"] > 0
+
+
+def gpu_count():
+    try:
+        return xf.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", [[], ["--serial", "--energy", "4", "--poisson", "0.4999"], ["--no-hint", "--energy", "5"]])
+def test_partitioned_gpu_matches_oracle(extra):
+    if gpu_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    out = run_ranks(2, ["--mode", "gpu", "--dims", "12", "6", "--substeps", "15"] + extra, 29633)
+    assert out["ok"], out["msg"]
+
+
+@pytest.mark.gpu
+def test_partition_single_rank_gpu():
+    """nRanks = 1 degenerates to the single-GPU schedule (no peers): still bit-exact."""
+    from oracle import bindings as ob
+    nodes, idx, hint = xf.GenerateTetBlock(6, 4, wonkiness=0.2)
+    part = xf.GeoPartitionCuda(nodes, idx, 1, 0, color_hint=hint)
+    st = xf.make_settings(energy=7)
+    part.Substep(st, np.float32(1 / 3000), 20)
+    X, V, w = part.get_state()
+    o = ob.OracleScene(nodes, idx)
+    o.set_order(part.get_order())
+    o.substep(ob.make_settings(energy=7), np.float32(1 / 3000), 20)
+    Xo, Vo, wo = o.get_state()
+    assert np.array_equal(X, Xo) and np.array_equal(V, Vo) and np.array_equal(w, wo)

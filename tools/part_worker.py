@@ -1,0 +1,139 @@
+"""Worker for the partitioned-mesh tests and measurements; launched once per rank by torch.distributed.run.
+
+  --mode emulate : CPU only (gloo).  Each rank builds the host-only partition plan (device = -1) and EMULATES the
+                   partitioned algorithm with the C oracle as the element solver and gloo send/recv for the halo
+                   lists; rank 0 compares the gathered result with the unpartitioned oracle (bit-exact).
+  --mode gpu     : one GPU per rank (nccl only moves the 128-byte IPC blobs); the library steps the mesh with
+                   in-kernel peer stores; rank 0 compares with the unpartitioned oracle (bit-exact) and prints timing.
+"""
+import argparse, json, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+from __graft_entry__ import load_package
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--mode", choices=["emulate", "gpu"], required=True)
+ap.add_argument("--dims", type=int, nargs=2, default=[8, 4])
+ap.add_argument("--wonk", type=float, default=0.2)
+ap.add_argument("--pattern", type=int, default=0)
+ap.add_argument("--energy", type=int, default=7)
+ap.add_argument("--serial", action="store_true")
+ap.add_argument("--poisson", type=float, default=0.5)
+ap.add_argument("--substeps", type=int, default=12)
+ap.add_argument("--no-hint", action="store_true")
+ap.add_argument("--check", type=int, default=1)
+ap.add_argument("--time-substeps", type=int, default=0)
+a = ap.parse_args()
+xf = load_package()
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+DT = np.float32(1.0 / 3000.0)
+nodes, idx, hint = xf.GenerateTetBlock(a.dims[0], a.dims[1], wonkiness=a.wonk, pattern=a.pattern)
+hint = None if (a.no_hint or a.pattern != 0) else hint
+kw = dict(energy=a.energy, simultaneous=not a.serial, poisson=a.poisson)
+
+
+def reference_state(order, n):
+    from oracle import bindings as ob
+    o = ob.OracleScene(nodes, idx)
+    o.set_order(order)
+    o.substep(ob.make_settings(**kw), DT, n)
+    return o.get_state()
+
+
+if a.mode == "emulate":
+    from oracle import bindings as ob
+    dist.init_process_group("gloo")
+    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=-1, color_hint=hint)
+    l2g = part.local_verts()
+    elems, cs = part.local_elements()
+    peers = part.peers()
+    tets = idx.reshape(-1, 5)[:, 1:]
+    g2l = np.full(part.nVGlobal, -1, dtype=np.int64)
+    g2l[l2g] = np.arange(part.nV)
+    local_stream = np.empty((part.nT, 5), dtype=np.uint32)
+    local_stream[:, 0] = 4
+    local_stream[:, 1:] = g2l[tets[elems]]
+    sub = ob.OracleScene(nodes.reshape(-1, 3)[l2g].reshape(-1), local_stream.reshape(-1))
+    sub.set_order(np.arange(part.nT, dtype=np.uint32))
+    w, flags = part.initial()
+    sub.set_state(w=w)
+    sub.set_flags(flags)
+    st = ob.make_settings(**kw)
+    for s in range(a.substeps):
+        sub.phase_predict(st, DT)
+        for c in range(part.nColors):
+            sub.phase_sweep(st, DT, int(cs[c]), int(cs[c + 1]))
+            X, V, ww = sub.get_state()
+            reqs, bufs = [], []
+            for slot, q in enumerate(peers):
+                snd = part.halo(c, slot, True)
+                rcv = part.halo(c, slot, False)
+                out = torch.from_numpy(np.ascontiguousarray(X[snd]))
+                inn = torch.empty((len(rcv), 3), dtype=torch.float64)
+                if len(snd):
+                    reqs.append(dist.isend(out, int(q), tag=c))
+                if len(rcv):
+                    reqs.append(dist.irecv(inn, int(q), tag=c))
+                bufs.append((rcv, inn, out))
+            for r in reqs:
+                r.wait()
+            for rcv, inn, _ in bufs:
+                if len(rcv):
+                    X[rcv] = inn.numpy()
+            sub.set_state(X=X)
+        sub.phase_post(st, DT)
+    X, V, ww = sub.get_state()
+    order = part.get_order()
+else:
+    torch.cuda.set_device(local_rank)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint)
+    blob = torch.from_numpy(part.ipc_export()).cuda()
+    allb = [torch.empty_like(blob) for _ in range(world)]
+    dist.all_gather(allb, blob)
+    part.ipc_connect(torch.stack(allb).cpu().numpy())
+    dist.barrier()
+    st = xf.make_settings(**kw)
+    for n in (1, a.substeps - 1):
+        part.Substep(st, DT, n)
+    X, V, ww = part.get_state()
+    l2g = part.local_verts()
+    order = part.get_order()
+    timing = None
+    if a.time_substeps:
+        dist.barrier()
+        part.Substep(st, DT, 5)
+        part.Sync()
+        dist.barrier()
+        t0 = time.perf_counter()
+        part.Substep(st, DT, a.time_substeps)
+        part.Sync()
+        el = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        timing = float(el.item())
+
+# gather to rank 0 and compare with the unpartitioned oracle
+gathered = [None] * world
+dist.gather_object((l2g, X, V, ww), gathered if rank == 0 else None, dst=0)
+if rank == 0:
+    nVg = nodes.size // 3
+    ok = True
+    msg = ""
+    if a.check:
+        Xo, Vo, wo = reference_state(order, a.substeps)
+        for r, (g, Xr, Vr, wr) in enumerate(gathered):
+            if not (np.array_equal(Xr, Xo[g]) and np.array_equal(Vr, Vo[g]) and np.array_equal(wr, wo[g])):
+                ok = False
+                msg = "rank %d differs: max|dX| = %.3e" % (r, np.abs(Xr - Xo[g]).max())
+    out = {"mode": a.mode, "world": world, "tets": int(idx.size // 5), "verts": int(nVg), "ok": ok, "msg": msg,
+           "shared_verts_rank0": int(sum(len(part.halo(c, s, True)) for c in range(part.nColors) for s in range(part.nPeers)))}
+    if a.mode == "gpu" and a.time_substeps:
+        out["us_per_substep"] = 1e6 * timing / a.time_substeps
+        out["element_substeps_per_s"] = (idx.size // 5) * a.time_substeps / timing
+    print("PART_RESULT " + json.dumps(out))
+dist.barrier()
+dist.destroy_process_group()

@@ -112,6 +112,11 @@ EXPORTS = [
     "xf_batch_create", "xf_batch_destroy", "xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count",
     "xf_batch_color_count", "xf_batch_get_order", "xf_batch_set_ground", "xf_batch_substep", "xf_batch_sync",
     "xf_batch_get_state", "xf_batch_set_state", "xf_batch_get_info",
+    "xf_part_create", "xf_part_destroy", "xf_part_local_vert_count", "xf_part_local_element_count", "xf_part_peer_count",
+    "xf_part_color_count", "xf_part_global_vert_count", "xf_part_global_element_count", "xf_part_get_local_verts",
+    "xf_part_get_local_elements", "xf_part_get_peers", "xf_part_get_halo", "xf_part_get_order", "xf_part_get_global_color_start",
+    "xf_part_get_initial", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
+    "xf_part_get_state", "xf_part_get_info",
 ]
 
 
@@ -163,6 +168,26 @@ def lib():
     L.xf_batch_get_state.argtypes = [vp, u32, u32, vp, vp, vp]
     L.xf_batch_set_state.argtypes = [vp, u32, u32, vp, vp, vp]
     L.xf_batch_get_info.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(u32), C.POINTER(C.c_uint64)]
+    L.xf_part_create.argtypes = [C.POINTER(CreateParams), vp, u32, vp, u32, u32, u32, C.POINTER(vp)]
+    L.xf_part_destroy.argtypes = [vp]
+    for n in ("xf_part_local_vert_count", "xf_part_local_element_count", "xf_part_peer_count", "xf_part_color_count",
+              "xf_part_global_vert_count", "xf_part_global_element_count"):
+        getattr(L, n).argtypes = [vp]
+        getattr(L, n).restype = u32
+    L.xf_part_get_local_verts.argtypes = [vp, vp]
+    L.xf_part_get_local_elements.argtypes = [vp, vp, vp]
+    L.xf_part_get_peers.argtypes = [vp, vp]
+    L.xf_part_get_halo.argtypes = [vp, u32, u32, i32, C.POINTER(u32), vp]
+    L.xf_part_get_order.argtypes = [vp, vp]
+    L.xf_part_get_global_color_start.argtypes = [vp, vp]
+    L.xf_part_get_initial.argtypes = [vp, vp, vp]
+    L.xf_part_ipc_export.argtypes = [vp, vp]
+    L.xf_part_ipc_connect.argtypes = [vp, vp]
+    L.xf_part_set_ground.argtypes = [vp, i32, f32, f32]
+    L.xf_part_substep.argtypes = [vp, vp, f32, u32]
+    L.xf_part_sync.argtypes = [vp]
+    L.xf_part_get_state.argtypes = [vp, vp, vp, vp]
+    L.xf_part_get_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     _lib = L
     return L
 
@@ -410,3 +435,118 @@ class GeoBatchCuda:
         g, b, s, l = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
         _check(lib().xf_batch_get_info(self._h, C.byref(g), C.byref(b), C.byref(s), C.byref(l)))
         return dict(groupThreads=g.value, blockThreads=b.value, smemBytes=s.value, launches=l.value)
+
+
+class GeoPartitionCuda:
+    """This rank's share of ONE mesh stepped on several GPUs (one process per GPU).  device=-1: host-only plan."""
+
+    IPC_BYTES = 128
+
+    def __init__(self, nodes, idx_stream, n_ranks, rank, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
+                 color_hint=None, stream=None):
+        L = lib()
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        p = CreateParams()
+        L.xf_default_create_params(C.byref(p))
+        p.device = device
+        p.density = density
+        p.autoResize = 1 if auto_resize else 0
+        p.precision = precision
+        p.stream = stream
+        if color_hint is not None:
+            color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)
+            p.colorHint = color_hint.ctypes.data
+            p.colorHintCount = color_hint.size
+        h = C.c_void_p()
+        self._h = None
+        _check(L.xf_part_create(C.byref(p), _vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, int(n_ranks), int(rank), C.byref(h)))
+        self._h = h
+        self.nRanks, self.rank = int(n_ranks), int(rank)
+        self.nV = L.xf_part_local_vert_count(h)
+        self.nT = L.xf_part_local_element_count(h)
+        self.nPeers = L.xf_part_peer_count(h)
+        self.nColors = L.xf_part_color_count(h)
+        self.nVGlobal = L.xf_part_global_vert_count(h)
+        self.nTGlobal = L.xf_part_global_element_count(h)
+
+    def close(self):
+        if self._h:
+            lib().xf_part_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def local_verts(self):
+        a = np.empty(self.nV, dtype=np.uint32)
+        _check(lib().xf_part_get_local_verts(self._h, _vp(a)))
+        return a
+
+    def local_elements(self):
+        e = np.empty(self.nT, dtype=np.uint32)
+        cs = np.empty(self.nColors + 1, dtype=np.uint32)
+        _check(lib().xf_part_get_local_elements(self._h, _vp(e), _vp(cs)))
+        return e, cs
+
+    def peers(self):
+        a = np.empty(self.nPeers, dtype=np.uint32)
+        _check(lib().xf_part_get_peers(self._h, _vp(a)))
+        return a
+
+    def halo(self, color, peer_slot, send):
+        n = C.c_uint32()
+        _check(lib().xf_part_get_halo(self._h, color, peer_slot, 1 if send else 0, C.byref(n), None))
+        a = np.empty(n.value, dtype=np.uint32)
+        _check(lib().xf_part_get_halo(self._h, color, peer_slot, 1 if send else 0, C.byref(n), _vp(a)))
+        return a
+
+    def get_order(self):
+        o = np.empty(self.nTGlobal, dtype=np.uint32)
+        _check(lib().xf_part_get_order(self._h, _vp(o)))
+        return o
+
+    def global_color_start(self):
+        cs = np.empty(self.nColors + 1, dtype=np.uint32)
+        _check(lib().xf_part_get_global_color_start(self._h, _vp(cs)))
+        return cs
+
+    def initial(self):
+        w = np.empty(self.nV, dtype=np.float32)
+        f = np.empty(self.nV, dtype=np.uint8)
+        _check(lib().xf_part_get_initial(self._h, _vp(w), _vp(f)))
+        return w, f
+
+    def ipc_export(self):
+        b = np.zeros(self.IPC_BYTES, dtype=np.uint8)
+        _check(lib().xf_part_ipc_export(self._h, _vp(b)))
+        return b
+
+    def ipc_connect(self, all_blobs):
+        all_blobs = np.ascontiguousarray(all_blobs, dtype=np.uint8).reshape(-1)
+        assert all_blobs.size == self.IPC_BYTES * self.nRanks
+        _check(lib().xf_part_ipc_connect(self._h, _vp(all_blobs)))
+
+    def set_ground(self, enabled, y0=0.0, friction=0.0):
+        _check(lib().xf_part_set_ground(self._h, 1 if enabled else 0, y0, friction))
+
+    def Substep(self, settings, dt, n=1):
+        _check(lib().xf_part_substep(self._h, C.byref(settings), float(dt), int(n)))
+
+    def Sync(self):
+        _check(lib().xf_part_sync(self._h))
+
+    def get_state(self):
+        X = np.empty((self.nV, 3), dtype=np.float64)
+        V = np.empty((self.nV, 3), dtype=np.float64)
+        w = np.empty(self.nV, dtype=np.float32)
+        _check(lib().xf_part_get_state(self._h, _vp(X), _vp(V), _vp(w)))
+        return X, V, w
+
+    def info(self):
+        l, e = C.c_uint64(), C.c_uint64()
+        _check(lib().xf_part_get_info(self._h, C.byref(l), C.byref(e)))
+        return dict(launches=l.value, epoch=e.value)

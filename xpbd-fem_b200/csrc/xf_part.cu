@@ -1,0 +1,503 @@
+// One mesh on several GPUs: each rank owns a slab of elements plus local copies of the vertices they touch
+// (plan: xf_partition.cpp).  Per phase (vertex phase, colour 0, colour 1, ...) every rank launches one kernel:
+//   prologue  thread 0 of each CTA waits until every peer has finished the previous phase (flag >= epoch - 1,
+//             ld.acquire.sys on flags the peers write into this GPU's memory over NVLink);
+//   body      the rank's elements of the colour; elements touching a shared vertex ALSO store the new position
+//             into the peers' copies (plain stores to cudaIpc-mapped peer memory: the halo exchange is fused
+//             into the sweep, no pack/send/unpack kernels and no NCCL on the data path);
+//   epilogue  the last CTA to finish issues a system-scope fence and writes `epoch` into each peer's flag slot.
+// A rank can therefore never run more than one phase ahead of a neighbour, which is exactly the dependence
+// the global colour order needs.  NCCL/torch.distributed (or anything else) is only needed to move the 128-byte
+// IPC handles at start-up.  Spin loops carry a bail-out so a protocol error reports XF_ERR_CUDA instead of
+// hanging the GPU.
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "xf_dispatch.cuh"
+#include "xf_element.cuh"
+#include "xf_partition.h"
+
+namespace xf {
+
+constexpr int kMaxPeers = 16;
+
+struct PartDevice {
+	DeviceScene local;            // local sub-mesh (local vertex numbering)
+	uint32_t nPeers;
+	uint32_t myRank;
+	VertexRec* peerXw[kMaxPeers]; // peers' vertex arrays (IPC-mapped)
+	unsigned long long* peerFlags[kMaxPeers]; // peers' flag arrays, indexed by sender rank
+	unsigned long long* myFlags;  // indexed by sender rank
+	uint32_t peerRank[kMaxPeers];
+	const uint32_t* shareStart;   // CSR over local vertices
+	const uint32_t* shareSlot;    //   peer slot
+	const uint32_t* shareRemoteIdx;
+	unsigned int* doneCounter;
+	unsigned int* errorFlag;
+};
+
+__device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void StoreReleaseSys(unsigned long long* p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void PhaseWait(const PartDevice& pd, unsigned long long epoch) {
+	if (threadIdx.x == 0) {
+		for (uint32_t s = 0; s < pd.nPeers; s++) {
+			const unsigned long long* f = pd.myFlags + pd.peerRank[s];
+			unsigned long long spins = 0;
+			while (LoadAcquireSys(f) + 1 < epoch) {
+				if (++spins > (1ull << 27)) { atomicExch(pd.errorFlag, 1u); break; } // ~seconds: protocol error, do not hang
+			}
+		}
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ void PhaseSignal(const PartDevice& pd, unsigned long long epoch) {
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		__threadfence_system();
+		const unsigned int prev = atomicAdd(pd.doneCounter, 1u);
+		if (prev == gridDim.x - 1) {
+			*pd.doneCounter = 0;
+			__threadfence_system();
+			for (uint32_t s = 0; s < pd.nPeers; s++) { StoreReleaseSys(pd.peerFlags[s] + pd.myRank, epoch); }
+		}
+	}
+}
+
+// Global store that mirrors position updates of shared vertices into the peers' copies.
+struct MirroredStore {
+	GlobalStore base;
+	const PartDevice* pd;
+	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return base.LoadX(i); }
+	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const {
+		base.StoreX(i, v);
+		const uint32_t b = __ldg(pd->shareStart + i), e = __ldg(pd->shareStart + i + 1);
+		for (uint32_t k = b; k < e; k++) { StoreVertex(pd->peerXw[__ldg(pd->shareSlot + k)], __ldg(pd->shareRemoteIdx + k), v); }
+	}
+	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { base.LoadO(i, o); }
+	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { base.LoadV(i, o); }
+	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const { base.StoreV(i, v); }
+};
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__global__ void __launch_bounds__(256) k_part_sweep(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, uint32_t begin,
+                                                    uint32_t ifaceEnd, uint32_t end, unsigned long long epoch) {
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	PhaseWait(pd, epoch);
+	const uint32_t e = begin + blockIdx.x * blockDim.x + threadIdx.x;
+	if (e < end) {
+		ElemRec rec;
+		LoadElement<kPrefactored, EXACT>(pd.local, e, rec);
+		if (e < ifaceEnd) {
+			const MirroredStore vs{ StoreOf(pd.local), &pd };
+			SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec);
+		} else {
+			const GlobalStore vs = StoreOf(pd.local);
+			SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec);
+		}
+	}
+	PhaseSignal(pd, epoch);
+}
+
+// vertex phase of the partitioned run: identical arithmetic to k_vertex_phase, on every local copy
+template <bool EXACT>
+__global__ void __launch_bounds__(256) k_part_vertex_phase(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, int doPost,
+                                                           int doPredict, unsigned long long epoch) {
+	typedef Op<EXACT> O;
+	PhaseWait(pd, epoch);
+	const DeviceScene& sc = pd.local;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < sc.nV) {
+		VertexRegs v = LoadVertex(sc.Xw, i);
+		double o[3], vel[3];
+		LoadD3(sc.O, i, o);
+		if (doPost) {
+			if (p.groundOn) {
+				double y0 = (double)p.groundY;
+				if (v.x[1] < y0) {
+					double keepT = (double)p.groundKeep;
+					v.x[1] = y0;
+					v.x[0] = O::dadd(o[0], O::dmul(O::dsub(v.x[0], o[0]), keepT));
+					v.x[2] = O::dadd(o[2], O::dmul(O::dsub(v.x[2], o[2]), keepT));
+				}
+			}
+			if (p.lockLeft && (v.flags & XF_VERT_LEFT)) { v.x[0] = o[0]; v.x[1] = o[1]; v.x[2] = o[2]; v.w = 0.0f; }
+			if (p.lockRight && (v.flags & XF_VERT_RIGHT)) {
+				double x0d[3];
+				LoadD3(sc.X0, i, x0d);
+				float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
+#pragma unroll
+				for (int r = 0; r < 3; r++) {
+					float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
+					double q = (double)O::add(p.origin[r], t);
+					v.x[r] = q;
+					o[r] = q;
+				}
+				v.w = 0.0f;
+			}
+			double invDt = (double)p.invDt;
+#pragma unroll
+			for (int k = 0; k < 3; k++) { vel[k] = O::dmul(O::dsub(v.x[k], o[k]), invDt); }
+		} else {
+			LoadD3(sc.V, i, vel);
+		}
+		if (doPredict) {
+			double g[3] = { (double)p.gdtX, (double)p.gdtY, 0.0 };
+			double keep = (double)p.keep;
+			double ddt = (double)p.dt;
+#pragma unroll
+			for (int k = 0; k < 3; k++) {
+				vel[k] = O::dadd(vel[k], g[k]);
+				vel[k] = O::dmul(vel[k], keep);
+				o[k] = v.x[k];
+				v.x[k] = O::dadd(v.x[k], O::dmul(vel[k], ddt));
+			}
+		}
+		StoreVertex(sc.Xw, i, v);
+		StoreD3(sc.O, i, o);
+		StoreD3(sc.V, i, vel);
+	}
+	PhaseSignal(pd, epoch);
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct PartRunner {
+	static cudaError_t Run(const PartDevice& pd, const SubstepParams& p, const std::vector<uint32_t>& colorStart, const std::vector<uint32_t>& ifaceEnd,
+	                       uint32_t nSubsteps, unsigned long long* epoch, cudaStream_t st, uint64_t* launches) {
+		if (DAMPED) { return cudaErrorNotSupported; }
+		const uint32_t nV = pd.local.nV;
+		const dim3 vgrid((nV + 255) / 256);
+		const uint32_t nC = (uint32_t)colorStart.size() - 1;
+		for (uint32_t s = 0; s < nSubsteps; s++) {
+			k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, s > 0 ? 1 : 0, 1, ++*epoch);
+			++*launches;
+			for (uint32_t c = 0; c < nC; c++) {
+				const uint32_t b = colorStart[c], e = colorStart[c + 1];
+				const uint32_t blocks = std::max<uint32_t>(1u, (e - b + 255) / 256); // an empty colour still takes part in the protocol
+				k_part_sweep<ENERGY, SIMUL, EXACT, false><<<dim3(blocks), 256, 0, st>>>(pd, p, b, ifaceEnd[c], e, ++*epoch);
+				++*launches;
+			}
+		}
+		k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, 1, 0, ++*epoch);
+		++*launches;
+		return cudaGetLastError();
+	}
+};
+
+}  // namespace xf
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+using namespace xf;
+
+struct xf_partition {
+	HostMesh mesh;    // the FULL mesh (every rank prepares it identically)
+	PartPlan plan;
+	PartDevice dev;
+	int device = -1;
+	int precision = XF_PRECISION_EXACT;
+	cudaStream_t stream = nullptr;
+	bool ownStream = false;
+	bool connected = false;
+	unsigned long long epoch = 0;
+	uint64_t launches = 0;
+	uint32_t groundOn = 0;
+	float groundY = 0.0f, groundFriction = 0.0f;
+	uint32_t* dShareStart = nullptr;
+	uint32_t* dShareSlot = nullptr;
+	uint32_t* dShareRemote = nullptr;
+	double* dPackX = nullptr;
+	double* dPackV = nullptr;
+	float* dPackW = nullptr;
+	std::vector<void*> openedPeers;
+};
+
+#define XFP_CUDA(call)                                         \
+	do {                                                       \
+		cudaError_t _e = (call);                               \
+		if (_e != cudaSuccess) { return FailCuda(_e, #call); } \
+	} while (0)
+
+namespace {
+template <typename T>
+cudaError_t UploadVecP(T** dst, const std::vector<T>& src) {
+	cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * std::max<size_t>(src.size(), 1));
+	if (e != cudaSuccess) { return e; }
+	return cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice);
+}
+struct IpcBlob { // 128 bytes moved between ranks by the host
+	cudaIpcMemHandle_t xw;
+	cudaIpcMemHandle_t flags;
+};
+static_assert(sizeof(IpcBlob) == 128, "IPC blob must be 128 bytes");
+
+int UploadPart(xf_partition* P) {
+	const HostMesh& m = P->mesh;
+	const PartPlan& pl = P->plan;
+	DeviceScene& d = P->dev.local;
+	const uint32_t nV = (uint32_t)pl.verts.size(), nT = (uint32_t)pl.elems.size();
+	d.nV = nV;
+	d.nT = nT;
+	d.nColors = (uint32_t)pl.colorStart.size() - 1;
+	std::vector<VertexRec> xw(nV);
+	std::vector<double4> x0(nV), zero(nV, double4{ 0, 0, 0, 0 });
+	for (uint32_t i = 0; i < nV; i++) {
+		const uint32_t g = pl.verts[i];
+		xw[i] = VertexRec{ m.X0[3 * (size_t)g], m.X0[3 * (size_t)g + 1], m.X0[3 * (size_t)g + 2], m.w[g], (uint32_t)m.flags[g] };
+		x0[i] = double4{ xw[i].x, xw[i].y, xw[i].z, 0.0 };
+	}
+	std::vector<uint4> eIdx(nT);
+	std::vector<float4> q0(nT), q1(nT), c0(nT);
+	std::vector<float2> q2(nT), c1(nT);
+	for (uint32_t k = 0; k < nT; k++) {
+		const uint32_t e = pl.elems[k];
+		const float* Q = &m.Qi[9 * (size_t)e];
+		eIdx[k] = uint4{ pl.localIdx[4 * (size_t)k], pl.localIdx[4 * (size_t)k + 1], pl.localIdx[4 * (size_t)k + 2], pl.localIdx[4 * (size_t)k + 3] };
+		q0[k] = float4{ Q[0], Q[1], Q[2], Q[3] };
+		q1[k] = float4{ Q[4], Q[5], Q[6], Q[7] };
+		q2[k] = float2{ Q[8], m.volume[e] };
+		c0[k] = float4{ m.QQ[3 * (size_t)e], m.QQ[3 * (size_t)e + 1], m.QQ[3 * (size_t)e + 2], m.QR[3 * (size_t)e] };
+		c1[k] = float2{ m.QR[3 * (size_t)e + 1], m.QR[3 * (size_t)e + 2] };
+	}
+	std::vector<uint32_t> slotOfRank(pl.nRanks, 0);
+	for (size_t s = 0; s < pl.peers.size(); s++) { slotOfRank[pl.peers[s]] = (uint32_t)s; }
+	std::vector<uint32_t> shareSlot(pl.sharePeerRank.size());
+	for (size_t k = 0; k < shareSlot.size(); k++) { shareSlot[k] = slotOfRank[pl.sharePeerRank[k]]; }
+	XFP_CUDA(UploadVecP(&d.Xw, xw));
+	XFP_CUDA(UploadVecP(&d.O, x0));
+	XFP_CUDA(UploadVecP(&d.X0, x0));
+	XFP_CUDA(UploadVecP(&d.V, zero));
+	XFP_CUDA(UploadVecP(&d.eIdx, eIdx));
+	XFP_CUDA(UploadVecP(&d.eQ0, q0));
+	XFP_CUDA(UploadVecP(&d.eQ1, q1));
+	XFP_CUDA(UploadVecP(&d.eQ2, q2));
+	XFP_CUDA(UploadVecP(&d.eC0, c0));
+	XFP_CUDA(UploadVecP(&d.eC1, c1));
+	XFP_CUDA(UploadVecP(&P->dShareStart, pl.shareStart));
+	XFP_CUDA(UploadVecP(&P->dShareSlot, shareSlot));
+	XFP_CUDA(UploadVecP(&P->dShareRemote, pl.shareRemoteIdx));
+	P->dev.shareStart = P->dShareStart;
+	P->dev.shareSlot = P->dShareSlot;
+	P->dev.shareRemoteIdx = P->dShareRemote;
+	XFP_CUDA(cudaMalloc((void**)&P->dev.myFlags, sizeof(unsigned long long) * 64));
+	XFP_CUDA(cudaMemset(P->dev.myFlags, 0, sizeof(unsigned long long) * 64));
+	XFP_CUDA(cudaMalloc((void**)&P->dev.doneCounter, 2 * sizeof(unsigned int)));
+	XFP_CUDA(cudaMemset(P->dev.doneCounter, 0, 2 * sizeof(unsigned int)));
+	P->dev.errorFlag = P->dev.doneCounter + 1;
+	XFP_CUDA(cudaMalloc((void**)&P->dPackX, sizeof(double) * 3 * std::max(nV, 1u)));
+	XFP_CUDA(cudaMalloc((void**)&P->dPackV, sizeof(double) * 3 * std::max(nV, 1u)));
+	XFP_CUDA(cudaMalloc((void**)&P->dPackW, sizeof(float) * std::max(nV, 1u)));
+	P->dev.nPeers = (uint32_t)pl.peers.size();
+	P->dev.myRank = pl.rank;
+	for (size_t s = 0; s < pl.peers.size(); s++) { P->dev.peerRank[s] = pl.peers[s]; }
+	return XF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount,
+                   uint32_t nRanks, uint32_t rank, xf_partition** outPart) {
+	if (!params || !outPart) { return Fail(XF_ERR_INVALID, "null params/outPart"); }
+	*outPart = nullptr;
+	if (params->abiVersion != XF_ABI_VERSION) { return Fail(XF_ERR_INVALID, "xf_create_params.abiVersion mismatch"); }
+	xf_partition* P = new (std::nothrow) xf_partition();
+	if (!P) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
+	std::string err;
+	int rc = PrepareMesh(nodeXYZ, nodeFloatCount, idxStream, idxCount, params->density, params->autoResize != 0, params->colorHint,
+	                     params->colorHintCount, &P->mesh, &err);
+	if (rc == XF_OK) { rc = BuildPartition(P->mesh, nRanks, rank, &P->plan, &err); }
+	if (rc != XF_OK) { delete P; return Fail(rc, err); }
+	if (P->plan.peers.size() > (size_t)kMaxPeers) { delete P; return Fail(XF_ERR_UNSUPPORTED, "a rank may share vertices with at most 16 other ranks"); }
+	memset(&P->dev, 0, sizeof(P->dev));
+	P->device = params->device;
+	P->precision = params->precision;
+	if (P->device >= 0) {
+		cudaError_t e = cudaSetDevice(P->device);
+		if (e != cudaSuccess) { delete P; return FailCuda(e, "cudaSetDevice"); }
+		if (params->stream) { P->stream = (cudaStream_t)params->stream; }
+		else {
+			e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
+			if (e != cudaSuccess) { delete P; return FailCuda(e, "cudaStreamCreate"); }
+			P->ownStream = true;
+		}
+		rc = UploadPart(P);
+		if (rc != XF_OK) { delete P; return rc; }
+		if (P->plan.peers.empty()) { P->connected = true; }
+	}
+	*outPart = P;
+	return XF_OK;
+}
+
+int xf_part_destroy(xf_partition* P) {
+	if (!P) { return XF_OK; }
+	if (P->device >= 0) {
+		cudaSetDevice(P->device);
+		if (P->stream) { cudaStreamSynchronize(P->stream); }
+		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
+		DeviceScene& d = P->dev.local;
+		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dev.myFlags,
+			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
+		for (void* p : ptrs) { if (p) { cudaFree(p); } }
+		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
+	}
+	delete P;
+	return XF_OK;
+}
+
+uint32_t xf_part_local_vert_count(const xf_partition* P) { return P ? (uint32_t)P->plan.verts.size() : 0; }
+uint32_t xf_part_local_element_count(const xf_partition* P) { return P ? (uint32_t)P->plan.elems.size() : 0; }
+uint32_t xf_part_peer_count(const xf_partition* P) { return P ? (uint32_t)P->plan.peers.size() : 0; }
+uint32_t xf_part_color_count(const xf_partition* P) { return P ? (uint32_t)P->plan.colorStart.size() - 1 : 0; }
+uint32_t xf_part_global_vert_count(const xf_partition* P) { return P ? P->mesh.nV : 0; }
+uint32_t xf_part_global_element_count(const xf_partition* P) { return P ? P->mesh.nT : 0; }
+
+int xf_part_get_local_verts(const xf_partition* P, uint32_t* localToGlobal) {
+	if (!P || !localToGlobal) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(localToGlobal, P->plan.verts.data(), sizeof(uint32_t) * P->plan.verts.size());
+	return XF_OK;
+}
+int xf_part_get_local_elements(const xf_partition* P, uint32_t* globalElementIds, uint32_t* colorStart) {
+	if (!P) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (globalElementIds) { memcpy(globalElementIds, P->plan.elems.data(), sizeof(uint32_t) * P->plan.elems.size()); }
+	if (colorStart) { memcpy(colorStart, P->plan.colorStart.data(), sizeof(uint32_t) * P->plan.colorStart.size()); }
+	return XF_OK;
+}
+int xf_part_get_peers(const xf_partition* P, uint32_t* peerRanks) {
+	if (!P || !peerRanks) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(peerRanks, P->plan.peers.data(), sizeof(uint32_t) * P->plan.peers.size());
+	return XF_OK;
+}
+int xf_part_get_halo(const xf_partition* P, uint32_t color, uint32_t peerSlot, int send, uint32_t* count, uint32_t* localVerts) {
+	if (!P || !count) { return Fail(XF_ERR_INVALID, "null argument"); }
+	const size_t nPeers = P->plan.peers.size();
+	if (color + 1 >= P->plan.colorStart.size() || peerSlot >= nPeers) { return Fail(XF_ERR_INVALID, "colour / peer slot out of range"); }
+	const std::vector<uint32_t>& start = send ? P->plan.sendStart : P->plan.recvStart;
+	const std::vector<uint32_t>& verts = send ? P->plan.sendVerts : P->plan.recvVerts;
+	const size_t k = color * nPeers + peerSlot;
+	*count = start[k + 1] - start[k];
+	if (localVerts) { memcpy(localVerts, verts.data() + start[k], sizeof(uint32_t) * *count); }
+	return XF_OK;
+}
+int xf_part_get_order(const xf_partition* P, uint32_t* fullOrder) {
+	if (!P || !fullOrder) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(fullOrder, P->mesh.order.data(), sizeof(uint32_t) * P->mesh.nT);
+	return XF_OK;
+}
+int xf_part_get_global_color_start(const xf_partition* P, uint32_t* colorStart) {
+	if (!P || !colorStart) { return Fail(XF_ERR_INVALID, "null argument"); }
+	memcpy(colorStart, P->mesh.colorStart.data(), sizeof(uint32_t) * P->mesh.colorStart.size());
+	return XF_OK;
+}
+int xf_part_get_initial(const xf_partition* P, float* w, uint8_t* flags) { // local vertices: global inverse masses / flags
+	if (!P) { return Fail(XF_ERR_INVALID, "null argument"); }
+	for (size_t i = 0; i < P->plan.verts.size(); i++) {
+		if (w) { w[i] = P->mesh.w[P->plan.verts[i]]; }
+		if (flags) { flags[i] = P->mesh.flags[P->plan.verts[i]]; }
+	}
+	return XF_OK;
+}
+
+int xf_part_ipc_export(xf_partition* P, void* out128) {
+	if (!P || !out128) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (P->device < 0) { return Fail(XF_ERR_CUDA, "host-only partition has no device memory"); }
+	XFP_CUDA(cudaSetDevice(P->device));
+	IpcBlob blob;
+	XFP_CUDA(cudaIpcGetMemHandle(&blob.xw, P->dev.local.Xw));
+	XFP_CUDA(cudaIpcGetMemHandle(&blob.flags, P->dev.myFlags));
+	memcpy(out128, &blob, sizeof(blob));
+	return XF_OK;
+}
+
+// allRanks: nRanks consecutive 128-byte blobs, blob r from rank r's xf_part_ipc_export.
+int xf_part_ipc_connect(xf_partition* P, const void* allRanks) {
+	if (!P || !allRanks) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (P->device < 0) { return Fail(XF_ERR_CUDA, "host-only partition has no device memory"); }
+	XFP_CUDA(cudaSetDevice(P->device));
+	const IpcBlob* blobs = (const IpcBlob*)allRanks;
+	for (size_t s = 0; s < P->plan.peers.size(); s++) {
+		const IpcBlob& b = blobs[P->plan.peers[s]];
+		void* xw = nullptr;
+		void* fl = nullptr;
+		XFP_CUDA(cudaIpcOpenMemHandle(&xw, b.xw, cudaIpcMemLazyEnablePeerAccess));
+		XFP_CUDA(cudaIpcOpenMemHandle(&fl, b.flags, cudaIpcMemLazyEnablePeerAccess));
+		P->openedPeers.push_back(xw);
+		P->openedPeers.push_back(fl);
+		P->dev.peerXw[s] = (VertexRec*)xw;
+		P->dev.peerFlags[s] = (unsigned long long*)fl;
+	}
+	P->connected = true;
+	return XF_OK;
+}
+
+int xf_part_set_ground(xf_partition* P, int enabled, float y0, float friction) {
+	if (!P) { return Fail(XF_ERR_INVALID, "null partition"); }
+	P->groundOn = enabled ? 1u : 0u;
+	P->groundY = y0;
+	P->groundFriction = friction;
+	return XF_OK;
+}
+
+int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n) {
+	if (!P || !st) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (P->device < 0) { return Fail(XF_ERR_CUDA, "host-only partition: there is no CPU compute path"); }
+	if (!P->connected) { return Fail(XF_ERR_INVALID, "xf_part_ipc_connect has not been called"); }
+	if (n == 0) { return XF_OK; }
+	XFP_CUDA(cudaSetDevice(P->device));
+	SubstepParams p;
+	std::string err;
+	int rc = FillSubstepParams(st, nullptr, dt, P->mesh, &p, &err);
+	if (rc != XF_OK) { return Fail(rc, err); }
+	if ((p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST) || p.doDamp || p.doPbdDamp || p.volumePasses) {
+		return Fail(XF_ERR_UNSUPPORTED, "the partitioned path implements the undamped main sweep only (damping / volume passes: single-GPU scenes)");
+	}
+	p.groundOn = P->groundOn;
+	p.groundY = P->groundY;
+	p.groundKeep = 1.0f - P->groundFriction;
+	p.handleCount = 0;
+	XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, P->plan.colorStart,
+	                                    P->plan.ifaceEnd, n, &P->epoch, P->stream, &P->launches));
+	return XF_OK;
+}
+
+int xf_part_sync(xf_partition* P) {
+	if (!P || P->device < 0) { return Fail(XF_ERR_INVALID, "null or host-only partition"); }
+	XFP_CUDA(cudaSetDevice(P->device));
+	XFP_CUDA(cudaStreamSynchronize(P->stream));
+	unsigned int flag = 0;
+	XFP_CUDA(cudaMemcpy(&flag, P->dev.errorFlag, sizeof(flag), cudaMemcpyDeviceToHost));
+	if (flag) { return Fail(XF_ERR_CUDA, "a peer did not reach the expected phase in time (halo protocol error)"); }
+	return XF_OK;
+}
+
+int xf_part_get_state(xf_partition* P, double* X, double* V, float* w) {
+	if (!P || P->device < 0) { return Fail(XF_ERR_INVALID, "null or host-only partition"); }
+	int rc = xf_part_sync(P);
+	if (rc != XF_OK) { return rc; }
+	const uint32_t nV = (uint32_t)P->plan.verts.size();
+	uint64_t dummy = 0;
+	XFP_CUDA(LaunchPackState(P->dev.local, X ? P->dPackX : nullptr, V ? P->dPackV : nullptr, w ? P->dPackW : nullptr, P->stream, &dummy));
+	if (X) { XFP_CUDA(cudaMemcpyAsync(X, P->dPackX, sizeof(double) * 3 * nV, cudaMemcpyDeviceToHost, P->stream)); }
+	if (V) { XFP_CUDA(cudaMemcpyAsync(V, P->dPackV, sizeof(double) * 3 * nV, cudaMemcpyDeviceToHost, P->stream)); }
+	if (w) { XFP_CUDA(cudaMemcpyAsync(w, P->dPackW, sizeof(float) * nV, cudaMemcpyDeviceToHost, P->stream)); }
+	XFP_CUDA(cudaStreamSynchronize(P->stream));
+	return XF_OK;
+}
+
+int xf_part_get_info(const xf_partition* P, uint64_t* launches, uint64_t* epoch) {
+	if (!P) { return Fail(XF_ERR_INVALID, "null partition"); }
+	if (launches) { *launches = P->launches; }
+	if (epoch) { *epoch = P->epoch; }
+	return XF_OK;
+}
+
+}  // extern "C"
