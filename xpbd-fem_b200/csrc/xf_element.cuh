@@ -85,34 +85,32 @@ struct VertexRegs {
 	float w;
 	uint32_t flags;
 };
+// 32-byte records move as ONE 256-bit L2 request (LDG.E.256 / STG.E.256, sm_100+) instead of two 128-bit ones:
+// the sweep is bound by L2 request/sector throughput in the bursts that follow each barrier.
+__device__ __forceinline__ void Load32B(const void* p, double& a, double& b, double& c, double& d) {
+	asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void Store32B(void* p, double a, double b, double c, double d) {
+	asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
 __device__ __forceinline__ VertexRegs LoadVertex(const VertexRec* Xw, uint32_t i) {
-	const double2* p = reinterpret_cast<const double2*>(Xw + i);
-	double2 a = __ldcg(p);
-	double2 b = __ldcg(p + 1);
 	VertexRegs v;
-	v.x[0] = a.x; v.x[1] = a.y; v.x[2] = b.x;
-	long long bits = __double_as_longlong(b.y);
+	double packed;
+	Load32B(Xw + i, v.x[0], v.x[1], v.x[2], packed);
+	long long bits = __double_as_longlong(packed);
 	v.w = __int_as_float((int)(bits & 0xffffffffll));
 	v.flags = (uint32_t)((unsigned long long)bits >> 32);
 	return v;
 }
 __device__ __forceinline__ void StoreVertex(VertexRec* Xw, uint32_t i, const VertexRegs& v) {
-	double2* p = reinterpret_cast<double2*>(Xw + i);
 	long long bits = (long long)(((unsigned long long)v.flags << 32) | (unsigned long long)(uint32_t)__float_as_int(v.w));
-	__stcg(p, make_double2(v.x[0], v.x[1]));
-	__stcg(p + 1, make_double2(v.x[2], __longlong_as_double(bits)));
+	Store32B(Xw + i, v.x[0], v.x[1], v.x[2], __longlong_as_double(bits));
 }
 __device__ __forceinline__ void LoadD3(const double4* A, uint32_t i, double* out) {
-	const double2* p = reinterpret_cast<const double2*>(A + i);
-	double2 a = __ldcg(p);
-	double2 b = __ldcg(p + 1);
-	out[0] = a.x; out[1] = a.y; out[2] = b.x;
+	double pad;
+	Load32B(A + i, out[0], out[1], out[2], pad);
 }
-__device__ __forceinline__ void StoreD3(double4* A, uint32_t i, const double* v) {
-	double2* p = reinterpret_cast<double2*>(A + i);
-	__stcg(p, make_double2(v[0], v[1]));
-	__stcg(p + 1, make_double2(v[2], 0.0));
-}
+__device__ __forceinline__ void StoreD3(double4* A, uint32_t i, const double* v) { Store32B(A + i, v[0], v[1], v[2], 0.0); }
 
 // Vertex-store policies: where an element's vertices live.  GlobalStore = the HBM/L2 arrays of a DeviceScene
 // (one mesh per device); SmemStore = one small scene resident in shared memory (batched scenes, xf_batch.cu).
