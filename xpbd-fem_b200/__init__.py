@@ -16,7 +16,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libxpbd_fem_b200.so")
+LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem_b200.so")  # override: kernel-variant experiments only
 
 XF_ABI_VERSION = 1
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5

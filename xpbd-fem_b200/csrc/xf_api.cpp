@@ -72,7 +72,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, d.eArea, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -95,31 +95,14 @@ int UploadScene(xf_scene* s) {
 	XF_CUDA(Upload(&d.X0, x0));
 	XF_CUDA(Upload(&d.V, zero));
 	// colour-sorted element planes
-	std::vector<uint4> eIdx(m.nT);
-	std::vector<float4> q0(m.nT), q1(m.nT), c0(m.nT);
-	std::vector<float2> q2(m.nT), c1(m.nT);
-	std::vector<float> area(m.nT);
 	std::vector<uint32_t> streamToSorted(m.nT);
-	for (uint32_t pos = 0; pos < m.nT; pos++) {
-		const uint32_t e = m.order[pos];
-		streamToSorted[e] = pos;
-		const uint32_t* v = &m.idx[4 * (size_t)e];
-		const float* Q = &m.Qi[9 * (size_t)e];
-		eIdx[pos] = uint4{ v[0], v[1], v[2], v[3] };
-		q0[pos] = float4{ Q[0], Q[1], Q[2], Q[3] };
-		q1[pos] = float4{ Q[4], Q[5], Q[6], Q[7] };
-		q2[pos] = float2{ Q[8], m.volume[e] };
-		c0[pos] = float4{ m.QQ[3 * (size_t)e], m.QQ[3 * (size_t)e + 1], m.QQ[3 * (size_t)e + 2], m.QR[3 * (size_t)e] };
-		c1[pos] = float2{ m.QR[3 * (size_t)e + 1], m.QR[3 * (size_t)e + 2] };
-		area[pos] = m.area[e];
-	}
-	XF_CUDA(Upload(&d.eIdx, eIdx));
-	XF_CUDA(Upload(&d.eQ0, q0));
-	XF_CUDA(Upload(&d.eQ1, q1));
-	XF_CUDA(Upload(&d.eQ2, q2));
-	XF_CUDA(Upload(&d.eC0, c0));
-	XF_CUDA(Upload(&d.eC1, c1));
-	XF_CUDA(Upload(&d.eArea, area));
+	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[m.order[pos]] = pos; }
+	PackedElements pk;
+	PackElements(m, m.order, nullptr, &pk);
+	XF_CUDA(Upload(&d.eA, pk.a));
+	XF_CUDA(Upload(&d.eB, pk.b));
+	XF_CUDA(Upload(&d.eC, pk.c));
+	XF_CUDA(Upload(&d.eArea, pk.area));
 	XF_CUDA(Upload(&d.streamToSorted, streamToSorted));
 	XF_CUDA(cudaMalloc((void**)&d.eScratch, sizeof(float) * m.nT));
 	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
@@ -444,7 +427,7 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 		out->gridBlocks = (uint32_t)s->shapes.begin()->second.gridBlocks;
 		out->blockThreads = (uint32_t)s->shapes.begin()->second.blockThreads;
 	}
-	out->elementRecordBytes = s->precision == XF_PRECISION_EXACT ? 80u : 56u;
+	out->elementRecordBytes = s->precision == XF_PRECISION_EXACT ? 80u : 64u; // +16 B only for prefactored energies in EXACT
 	out->schedule = (uint32_t)s->schedule;
 	out->kernelLaunches = s->launches;
 	out->l2Bytes = s->l2Bytes;

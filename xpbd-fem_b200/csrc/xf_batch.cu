@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_batch_substeps(const __grid_constant__ 
 					for (uint32_t c = 0; c < bd.nColors; c++) {
 						const uint32_t b = max(bd.colorStart[c], lo), end = min(bd.colorStart[c + 1], hi);
 						if (active) {
-							for (uint32_t e = b + t; e < end; e += T) { PbdDampElement<EXACT>(st, p, __ldg(bd.mesh.eArea + e), __ldg(bd.mesh.eIdx + e)); }
+							for (uint32_t e = b + t; e < end; e += T) { PbdDampElement<EXACT>(st, p, __ldg(bd.mesh.eArea + e), LoadElementIdx(bd.mesh, e)); }
 						}
 						GroupSync(T);
 					}
@@ -258,7 +258,7 @@ cudaError_t UploadVec(T** dst, const std::vector<T>& src) {
 void FreeBatch(xf_batch* b) {
 	cudaSetDevice(b->device);
 	DeviceScene& d = b->dev.mesh;
-	void* ptrs[] = { d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, d.eArea, b->dev.X, b->dev.V, b->dev.W, b->dConsts, b->dFlags };
+	void* ptrs[] = { d.X0, d.eA, d.eB, d.eC, d.eArea, b->dev.X, b->dev.V, b->dev.W, b->dConsts, b->dFlags };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (b->ownStream && b->stream) { cudaStreamDestroy(b->stream); }
 }
@@ -320,27 +320,12 @@ int xf_batch_create(const xf_create_params* params, const float* nodeXYZ, uint32
 	for (size_t c = 0; c < m.colorStart.size(); c++) { d.colorStart[c] = m.colorStart[c]; }
 	d.mesh.nV = m.nV;
 	d.mesh.nT = m.nT;
-	std::vector<uint4> eIdx(m.nT);
-	std::vector<float4> q0(m.nT), q1(m.nT), c0(m.nT);
-	std::vector<float2> q2(m.nT), c1(m.nT);
-	std::vector<float> area(m.nT);
-	for (uint32_t pos = 0; pos < m.nT; pos++) {
-		const uint32_t el = m.order[pos];
-		const uint32_t* v = &m.idx[4 * (size_t)el];
-		const float* Q = &m.Qi[9 * (size_t)el];
-		eIdx[pos] = uint4{ v[0], v[1], v[2], v[3] };
-		q0[pos] = float4{ Q[0], Q[1], Q[2], Q[3] };
-		q1[pos] = float4{ Q[4], Q[5], Q[6], Q[7] };
-		q2[pos] = float2{ Q[8], m.volume[el] };
-		c0[pos] = float4{ m.QQ[3 * (size_t)el], m.QQ[3 * (size_t)el + 1], m.QQ[3 * (size_t)el + 2], m.QR[3 * (size_t)el] };
-		c1[pos] = float2{ m.QR[3 * (size_t)el + 1], m.QR[3 * (size_t)el + 2] };
-		area[pos] = m.area[el];
-	}
+	PackedElements pk;
+	PackElements(m, m.order, nullptr, &pk);
 	std::vector<double4> x0(m.nV);
 	for (uint32_t i = 0; i < m.nV; i++) { x0[i] = double4{ m.X0[3 * (size_t)i], m.X0[3 * (size_t)i + 1], m.X0[3 * (size_t)i + 2], 0.0 }; }
-	bool ok = UploadVec(&d.mesh.eIdx, eIdx) == cudaSuccess && UploadVec(&d.mesh.eQ0, q0) == cudaSuccess && UploadVec(&d.mesh.eQ1, q1) == cudaSuccess &&
-	          UploadVec(&d.mesh.eQ2, q2) == cudaSuccess && UploadVec(&d.mesh.eC0, c0) == cudaSuccess && UploadVec(&d.mesh.eC1, c1) == cudaSuccess &&
-	          UploadVec(&d.mesh.eArea, area) == cudaSuccess && UploadVec(&d.mesh.X0, x0) == cudaSuccess && UploadVec(&b->dFlags, m.flags) == cudaSuccess;
+	bool ok = UploadVec(&d.mesh.eA, pk.a) == cudaSuccess && UploadVec(&d.mesh.eB, pk.b) == cudaSuccess && UploadVec(&d.mesh.eC, pk.c) == cudaSuccess &&
+	          UploadVec(&d.mesh.eArea, pk.area) == cudaSuccess && UploadVec(&d.mesh.X0, x0) == cudaSuccess && UploadVec(&b->dFlags, m.flags) == cudaSuccess;
 	d.flags = b->dFlags;
 	const size_t n3 = 3 * (size_t)m.nV;
 	ok = ok && cudaMalloc((void**)&d.X, sizeof(double) * n3 * nScenes) == cudaSuccess && cudaMalloc((void**)&d.V, sizeof(double) * n3 * nScenes) == cudaSuccess &&

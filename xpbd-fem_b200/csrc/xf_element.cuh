@@ -49,24 +49,28 @@ struct ElemRec {
 	float QQ[3], QR[3];
 };
 
-__device__ __forceinline__ float4 ldg_f4(const float4* p) { return __ldg(p); }
+// 256-bit read-only load (element planes never change after upload).
+__device__ __forceinline__ void LoadConst32B(const void* p, uint32_t (&r)[8]) {
+	asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+	             : "l"(p));
+}
 
 template <bool NEED_PREFACTORED, bool EXACT>
 __device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, ElemRec& r) {
-	r.idx = __ldg(sc.eIdx + e);
-	float4 a = __ldg(sc.eQ0 + e);
-	float4 b = __ldg(sc.eQ1 + e);
-	float2 c = __ldg(sc.eQ2 + e);
-	r.Qi[0][0] = a.x; r.Qi[0][1] = a.y; r.Qi[0][2] = a.z;
-	r.Qi[1][0] = a.w; r.Qi[1][1] = b.x; r.Qi[1][2] = b.y;
-	r.Qi[2][0] = b.z; r.Qi[2][1] = b.w; r.Qi[2][2] = c.x;
-	r.volume = c.y;
+	uint32_t a[8], b[8];
+	LoadConst32B(sc.eA + e, a);
+	LoadConst32B(sc.eB + e, b);
+	r.idx = make_uint4(a[0], a[1], a[2], a[3]);
+	r.Qi[0][0] = __uint_as_float(a[4]); r.Qi[0][1] = __uint_as_float(a[5]); r.Qi[0][2] = __uint_as_float(a[6]);
+	r.Qi[1][0] = __uint_as_float(a[7]); r.Qi[1][1] = __uint_as_float(b[0]); r.Qi[1][2] = __uint_as_float(b[1]);
+	r.Qi[2][0] = __uint_as_float(b[2]); r.Qi[2][1] = __uint_as_float(b[3]); r.Qi[2][2] = __uint_as_float(b[4]);
+	r.volume = __uint_as_float(b[5]);
 	if (NEED_PREFACTORED) {
 		if (EXACT) {
-			float4 q = __ldg(sc.eC0 + e);
-			float2 s = __ldg(sc.eC1 + e);
-			r.QQ[0] = q.x; r.QQ[1] = q.y; r.QQ[2] = q.z;
-			r.QR[0] = q.w; r.QR[1] = s.x; r.QR[2] = s.y;
+			float4 q = __ldg(sc.eC + e);
+			r.QQ[0] = __uint_as_float(b[6]); r.QQ[1] = __uint_as_float(b[7]); r.QQ[2] = q.x;
+			r.QR[0] = q.y; r.QR[1] = q.z; r.QR[2] = q.w;
 		} else {
 			// QQ_i = |col_i(Qi)|^2, QR = 2 col_i . col_j  (what Fem.cpp:131-161 integrates, up to rounding)
 			r.QQ[0] = Op<false>::dot(r.Qi[0], r.Qi[0]);
@@ -78,6 +82,7 @@ __device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, E
 		}
 	}
 }
+__device__ __forceinline__ uint4 LoadElementIdx(const DeviceScene& sc, uint32_t e) { return __ldg(reinterpret_cast<const uint4*>(sc.eA + e)); }
 
 // Vertex gather: L2-only loads (ld.global.cg) because other SMs rewrite positions between colours.
 struct VertexRegs {

@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(256) k_vertex_phase(const DeviceScene sc, cons
 template <int KIND, int ENERGY, bool EXACT>
 __device__ __forceinline__ void SweepLoad(const DeviceScene& sc, uint32_t e, ElemRec& rec) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
-	if (KIND == 3) { rec.idx = __ldg(sc.eIdx + e); return; }
+	if (KIND == 3) { rec.idx = LoadElementIdx(sc, e); return; }
 	LoadElement<(KIND != 1) && kPrefactored, EXACT>(sc, e, rec);
 }
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
@@ -173,8 +173,14 @@ __device__ __forceinline__ void SweepRange(const DeviceScene& sc, const SubstepP
 	if (NEXT_KIND >= 0 && nb + slot < nend) { SweepLoad<(NEXT_KIND < 0 ? 0 : NEXT_KIND), ENERGY, EXACT>(sc, nb + slot, rec); }
 }
 
+#ifndef XF_PERSIST_THREADS
+#define XF_PERSIST_THREADS 256
+#endif
+#ifndef XF_PERSIST_MIN_BLOCKS
+#define XF_PERSIST_MIN_BLOCKS 2
+#endif
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-__global__ void __launch_bounds__(256, 2) k_substeps_persistent(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps) {
+__global__ void __launch_bounds__(XF_PERSIST_THREADS, XF_PERSIST_MIN_BLOCKS) k_substeps_persistent(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps) {
 	cg::grid_group grid = cg::this_grid();
 	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t gsize = gridDim.x * blockDim.x;
@@ -252,7 +258,7 @@ __global__ void __launch_bounds__(256) k_element_volumes(const DeviceScene sc) {
 	uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= sc.nT) { return; }
 	uint32_t e = sc.streamToSorted[s];
-	uint4 idx = __ldg(sc.eIdx + e);
+	uint4 idx = LoadElementIdx(sc, e);
 	VertexRegs v[4] = { LoadVertex(sc.Xw, idx.x), LoadVertex(sc.Xw, idx.y), LoadVertex(sc.Xw, idx.z), LoadVertex(sc.Xw, idx.w) };
 	float P[3][3];
 	Edges<true>(v, P);
@@ -447,7 +453,7 @@ cudaError_t QueryLaunchShape(int device, uint32_t energy, bool exact, LaunchShap
 	cudaError_t e = cudaGetDeviceProperties(&prop, device);
 	if (e != cudaSuccess) { return e; }
 	shape->smCount = prop.multiProcessorCount;
-	shape->blockThreads = 256;
+	shape->blockThreads = XF_PERSIST_THREADS;
 	// the most register-hungry variants bound the co-resident grid for all of them
 	int worst = 1 << 30;
 	for (int simul = 0; simul < 2; simul++) {
@@ -543,10 +549,37 @@ __device__ __forceinline__ void GridBarrierV(unsigned int* counter, unsigned int
 	}
 	__syncthreads();
 }
+// Two-level barrier: CTAs arrive on one of `groups` counters (separate 128-byte lines => separate L2 slices);
+// the last arriver of a group arrives on the root; the last root arriver bumps the release word everybody polls.
+__device__ __forceinline__ void GridBarrierTree(unsigned int* base, unsigned int& epoch, uint32_t groupSize) {
+	__syncthreads();
+	epoch += 1;
+	if (threadIdx.x == 0) {
+		const uint32_t nGroups = (gridDim.x + groupSize - 1) / groupSize;
+		const uint32_t g = blockIdx.x / groupSize;
+		const uint32_t members = min(groupSize, gridDim.x - g * groupSize);
+		unsigned int* groupCtr = base + 32 * (2 + g);
+		unsigned int* rootCtr = base + 32;
+		unsigned int* release = base;
+		__threadfence();
+		if (atomicAdd(groupCtr, 1u) == members * epoch - 1) {
+			if (atomicAdd(rootCtr, 1u) == nGroups * epoch - 1) {
+				asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(release), "r"(epoch) : "memory");
+			}
+		}
+		unsigned int v;
+		do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(release) : "memory"); } while (v < epoch);
+		asm volatile("fence.acq_rel.gpu;" ::: "memory");
+	}
+	__syncthreads();
+}
 template <int VARIANT>
 __global__ void __launch_bounds__(256, 2) k_barrier_only(unsigned int* counter, uint32_t iterations) {
 	unsigned int target = 0;
-	if (VARIANT == 4) {
+	if (VARIANT >= 5) {
+		const uint32_t groupSize = VARIANT == 5 ? 8 : (VARIANT == 6 ? 16 : 32);
+		for (uint32_t i = 0; i < iterations; i++) { GridBarrierTree(counter, target, groupSize); }
+	} else if (VARIANT == 4) {
 		cg::grid_group g = cg::this_grid();
 		for (uint32_t i = 0; i < iterations; i++) { g.sync(); }
 	} else {
@@ -560,7 +593,7 @@ extern "C" int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int
 	cudaDeviceProp prop;
 	cudaGetDeviceProperties(&prop, device);
 	unsigned int* counter = nullptr;
-	cudaMalloc(&counter, 128);
+	cudaMalloc(&counter, 128 * 64);
 	cudaEvent_t a, b;
 	cudaEventCreate(&a);
 	cudaEventCreate(&b);
@@ -571,10 +604,13 @@ extern "C" int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int
 	case 1: fn = (const void*)xf::k_barrier_only<1>; break;
 	case 2: fn = (const void*)xf::k_barrier_only<2>; break;
 	case 3: fn = (const void*)xf::k_barrier_only<3>; break;
-	default: fn = (const void*)xf::k_barrier_only<4>; break;
+	case 4: fn = (const void*)xf::k_barrier_only<4>; break;
+	case 5: fn = (const void*)xf::k_barrier_only<5>; break;
+	case 6: fn = (const void*)xf::k_barrier_only<6>; break;
+	default: fn = (const void*)xf::k_barrier_only<7>; break;
 	}
 	for (int rep = 0; rep < 5; rep++) {
-		cudaMemset(counter, 0, 128);
+		cudaMemset(counter, 0, 128 * 64);
 		void* args[] = { (void*)&counter, (void*)&iterations };
 		cudaEventRecord(a);
 		cudaError_t e = cudaLaunchCooperativeKernel(fn, dim3(prop.multiProcessorCount * blocksPerSm), dim3(threads), args, 0, 0);

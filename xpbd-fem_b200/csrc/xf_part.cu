@@ -255,19 +255,8 @@ int UploadPart(xf_partition* P) {
 		xw[i] = VertexRec{ m.X0[3 * (size_t)g], m.X0[3 * (size_t)g + 1], m.X0[3 * (size_t)g + 2], m.w[g], (uint32_t)m.flags[g] };
 		x0[i] = double4{ xw[i].x, xw[i].y, xw[i].z, 0.0 };
 	}
-	std::vector<uint4> eIdx(nT);
-	std::vector<float4> q0(nT), q1(nT), c0(nT);
-	std::vector<float2> q2(nT), c1(nT);
-	for (uint32_t k = 0; k < nT; k++) {
-		const uint32_t e = pl.elems[k];
-		const float* Q = &m.Qi[9 * (size_t)e];
-		eIdx[k] = uint4{ pl.localIdx[4 * (size_t)k], pl.localIdx[4 * (size_t)k + 1], pl.localIdx[4 * (size_t)k + 2], pl.localIdx[4 * (size_t)k + 3] };
-		q0[k] = float4{ Q[0], Q[1], Q[2], Q[3] };
-		q1[k] = float4{ Q[4], Q[5], Q[6], Q[7] };
-		q2[k] = float2{ Q[8], m.volume[e] };
-		c0[k] = float4{ m.QQ[3 * (size_t)e], m.QQ[3 * (size_t)e + 1], m.QQ[3 * (size_t)e + 2], m.QR[3 * (size_t)e] };
-		c1[k] = float2{ m.QR[3 * (size_t)e + 1], m.QR[3 * (size_t)e + 2] };
-	}
+	PackedElements pk;
+	PackElements(m, pl.elems, pl.localIdx.data(), &pk);
 	std::vector<uint32_t> slotOfRank(pl.nRanks, 0);
 	for (size_t s = 0; s < pl.peers.size(); s++) { slotOfRank[pl.peers[s]] = (uint32_t)s; }
 	std::vector<uint32_t> shareSlot(pl.sharePeerRank.size());
@@ -276,12 +265,9 @@ int UploadPart(xf_partition* P) {
 	XFP_CUDA(UploadVecP(&d.O, x0));
 	XFP_CUDA(UploadVecP(&d.X0, x0));
 	XFP_CUDA(UploadVecP(&d.V, zero));
-	XFP_CUDA(UploadVecP(&d.eIdx, eIdx));
-	XFP_CUDA(UploadVecP(&d.eQ0, q0));
-	XFP_CUDA(UploadVecP(&d.eQ1, q1));
-	XFP_CUDA(UploadVecP(&d.eQ2, q2));
-	XFP_CUDA(UploadVecP(&d.eC0, c0));
-	XFP_CUDA(UploadVecP(&d.eC1, c1));
+	XFP_CUDA(UploadVecP(&d.eA, pk.a));
+	XFP_CUDA(UploadVecP(&d.eB, pk.b));
+	XFP_CUDA(UploadVecP(&d.eC, pk.c));
 	XFP_CUDA(UploadVecP(&P->dShareStart, pl.shareStart));
 	XFP_CUDA(UploadVecP(&P->dShareSlot, shareSlot));
 	XFP_CUDA(UploadVecP(&P->dShareRemote, pl.shareRemoteIdx));
@@ -345,7 +331,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eIdx, d.eQ0, d.eQ1, d.eQ2, d.eC0, d.eC1, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }

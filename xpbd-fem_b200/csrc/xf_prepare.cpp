@@ -295,6 +295,25 @@ int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* i
 	return XF_OK;
 }
 
+void PackElements(const HostMesh& m, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out) {
+	const size_t n = elems.size();
+	out->a.resize(n);
+	out->b.resize(n);
+	out->c.resize(n);
+	out->area.resize(n);
+	for (size_t k = 0; k < n; k++) {
+		const uint32_t e = elems[k];
+		const uint32_t* v = localIdx ? &localIdx[4 * k] : &m.idx[4 * (size_t)e];
+		const float* Q = &m.Qi[9 * (size_t)e];
+		const float* qq = &m.QQ[3 * (size_t)e];
+		const float* qr = &m.QR[3 * (size_t)e];
+		out->a[k] = ElemRecA{ { v[0], v[1], v[2], v[3] }, { Q[0], Q[1], Q[2], Q[3] } };
+		out->b[k] = ElemRecB{ { Q[4], Q[5], Q[6], Q[7], Q[8] }, m.volume[e], { qq[0], qq[1] } };
+		out->c[k] = float4{ qq[2], qr[0], qr[1], qr[2] };
+		out->area[k] = m.area[e];
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Per-call constants.
 // ------------------------------------------------------------------------------------------------

@@ -18,20 +18,29 @@ namespace xf {
 // Vertices (AoS, one 32-byte L2 sector per vertex so an element gather costs exactly 4 sectors):
 //   VertexRec  Xw[nV]   { double x, y, z; float w; uint32 flags }   position + inverse mass + lock flags
 //   double4    O[nV], V[nV], X0[nV]                                  (.w unused)
-// Elements (SoA planes, sorted by colour then by original index, so a warp streams each plane with
-// fully coalesced 16/8-byte loads):
-//   uint4  eIdx[nT]        vertex indices
-//   float4 eQ0[nT]         Qi[0][0] Qi[0][1] Qi[0][2] Qi[1][0]     (Qi column-major like the reference's mat3)
-//   float4 eQ1[nT]         Qi[1][1] Qi[1][2] Qi[2][0] Qi[2][1]
-//   float2 eQ2[nT]         Qi[2][2] volume                          -> 56 B/element (XF_PRECISION_FAST)
-//   float4 eC0[nT]         QQ0 QQ1 QQ2 QR0                          (+24 B: the reference's own prefactored
-//   float2 eC1[nT]         QR1 QR2                                   coefficients, XF_PRECISION_EXACT only)
-//   float  eArea[nT]       surfaceArea (PbdDamp only)
+// Elements: three planes sorted by colour then by original index.  The sweep is bound by L2 *requests*, so a
+// record is fetched with two 256-bit loads (+ one 128-bit load when the reference's own prefactored
+// coefficients are needed), each lane reading whole 32-byte sectors:
+//   ElemRecA eA[nT]   32 B   idx[4]; Qi[0][0] Qi[0][1] Qi[0][2] Qi[1][0]      (Qi column-major like mat3)
+//   ElemRecB eB[nT]   32 B   Qi[1][1] Qi[1][2] Qi[2][0] Qi[2][1] Qi[2][2]; volume; QQ0 QQ1
+//   float4   eC[nT]   16 B   QQ2 QR0 QR1 QR2         (XF_PRECISION_EXACT + prefactored energies only)
+//   float    eArea[nT]       surfaceArea (PbdDamp only)
+// => 64 B (fast / non-prefactored) or 80 B (exact prefactored) streamed per element per sweep.
 // ------------------------------------------------------------------------------------------------
 struct alignas(32) VertexRec {
 	double x, y, z;
 	float w;
 	uint32_t flags;
+};
+
+struct alignas(32) ElemRecA {
+	uint32_t idx[4];
+	float q[4];
+};
+struct alignas(32) ElemRecB {
+	float q[5];
+	float volume;
+	float qq01[2];
 };
 
 struct DeviceScene {
@@ -40,12 +49,9 @@ struct DeviceScene {
 	double4* O = nullptr;
 	double4* V = nullptr;
 	double4* X0 = nullptr;
-	uint4* eIdx = nullptr;
-	float4* eQ0 = nullptr;
-	float4* eQ1 = nullptr;
-	float2* eQ2 = nullptr;
-	float4* eC0 = nullptr;
-	float2* eC1 = nullptr;
+	ElemRecA* eA = nullptr;
+	ElemRecB* eB = nullptr;
+	float4* eC = nullptr;
 	float* eArea = nullptr;
 	float* eScratch = nullptr;      // nT floats (per-element volume terms)
 	double* statScratch = nullptr;  // reduction outputs
@@ -134,6 +140,15 @@ struct HostMesh {
 // Returns 0 or an xf_status; on failure `err` holds the message.
 int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density,
                 bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err);
+// Element planes for the elements `elems` (global ids, in device order); `localIdx` (4 per element) replaces the
+// mesh's vertex ids when the device uses a local vertex numbering (partitioned meshes), else nullptr.
+struct PackedElements {
+	std::vector<ElemRecA> a;
+	std::vector<ElemRecB> b;
+	std::vector<float4> c;
+	std::vector<float> area;
+};
+void PackElements(const HostMesh& mesh, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out);
 int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
                       std::string* err);
 
