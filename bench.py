@@ -321,8 +321,18 @@ def main():
         ach_hbm = (nT * sub * b_hbm) / (kernel_ms * 1e-3) / 1e9
         ach_l2 = (nT * sub * b_l2) / (kernel_ms * 1e-3) / 1e9
         ws = 56 * nT + 48 * nV
+        traffic = None  # dram__bytes_read+write of ONE launch of the dominant kernel, from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+                tj = json.load(f)
+            if (args.cells, args.precision, args.energy, args.schedule) == (55, "exact", "yeohskinfast", "persistent"):
+                traffic = tj["dram_bytes_per_element_substep"] * nT * sub  # per launch of `sub` substeps
+        except Exception:
+            traffic = None
         roofline = {
-            "bound": "hbm", "achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "traffic": None,
+            "bound": "hbm", "achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "traffic": traffic,
+            "traffic_source": "profiles/r1_traffic.json (ncu --set full, same kernel and workload)" if traffic else None,
+            "algorithmic_bytes_per_launch": nT * sub * b_hbm,
             "peak_source": peak_src, "kernel": "k_substeps_persistent" if args.schedule == "persistent" else "k_sweep_color (x colours)",
             "bytes_per_element_substep": b_hbm, "units_per_launch": per_launch_units, "kernel_ms": kernel_ms,
             "achieved_l2_gbs": ach_l2, "bytes_per_element_substep_l2": b_l2, "working_set_bytes": ws, "l2_bytes": info["l2Bytes"],
