@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=55, help="block is cells^3 hexes -> 6*cells^3 tets")
     ap.add_argument("--substeps-per-step", type=int, default=50)
     ap.add_argument("--precision", choices=["exact", "fast"], default="exact")
-    ap.add_argument("--schedule", choices=["persistent", "per_color"], default="persistent")
+    ap.add_argument("--schedule", choices=["bricks", "persistent", "per_color"], default="persistent")
     ap.add_argument("--energy", choices=["yeohskinfast", "mixedsel", "mixed", "yeohskin"], default="yeohskinfast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hint", action="store_true", help="use the generic colouring instead of the lattice 24-colouring")
@@ -118,7 +118,7 @@ def make_scene(xf, args, device, stream):
     nodes, idx, hint = xf.GenerateTetBlock(args.cells, args.cells)
     geo = xf.GeoLinear3dCuda(nodes, idx, device=device, stream=stream,
                              precision=xf.PRECISION_EXACT if args.precision == "exact" else xf.PRECISION_FAST,
-                             schedule=xf.SCHEDULE_PERSISTENT if args.schedule == "persistent" else xf.SCHEDULE_LAUNCH_PER_COLOR,
+                             schedule={"bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
                              color_hint=None if args.no_hint else hint)
     y_min = float(nodes.reshape(-1, 3)[:, 1].min())
     geo.set_ground(True, y_min - 1.0e-3, 0.0)
@@ -316,7 +316,7 @@ def main():
         b_l2 = 184.0
         kernel_ms = ms_max / args.steps  # persistent schedule: the whole step is ONE launch of the dominant kernel
         per_launch_units = nT * sub
-        if args.schedule != "persistent":
+        if args.schedule == "per_color":
             per_launch_units = None
         ach_hbm = (nT * sub * b_hbm) / (kernel_ms * 1e-3) / 1e9
         ach_l2 = (nT * sub * b_l2) / (kernel_ms * 1e-3) / 1e9
@@ -325,7 +325,7 @@ def main():
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
                 tj = json.load(f)
-            if (args.cells, args.precision, args.energy, args.schedule) == (55, "exact", "yeohskinfast", "persistent"):
+            if (args.cells, args.precision, args.energy, args.schedule) == (55, "exact", "yeohskinfast", tj.get("schedule", "persistent")):
                 traffic = tj["dram_bytes_per_element_substep"] * nT * sub  # per launch of `sub` substeps
         except Exception:
             traffic = None
@@ -333,7 +333,7 @@ def main():
             "bound": "hbm", "achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "traffic": traffic,
             "traffic_source": "profiles/r1_traffic.json (ncu --set full, same kernel and workload)" if traffic else None,
             "algorithmic_bytes_per_launch": nT * sub * b_hbm,
-            "peak_source": peak_src, "kernel": "k_substeps_persistent" if args.schedule == "persistent" else "k_sweep_color (x colours)",
+            "peak_source": peak_src, "kernel": {"bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent", "per_color": "k_sweep_color (x colours)"}[args.schedule],
             "bytes_per_element_substep": b_hbm, "units_per_launch": per_launch_units, "kernel_ms": kernel_ms,
             "achieved_l2_gbs": ach_l2, "bytes_per_element_substep_l2": b_l2, "working_set_bytes": ws, "l2_bytes": info["l2Bytes"],
             "headline_rule": "L2 figure iff working set <= l2/2 (SURVEY 8d); here %s" % ("L2" if ws <= info["l2Bytes"] / 2 else "HBM"),

@@ -16,7 +16,7 @@ build()
 xf = load_package()
 pytestmark = pytest.mark.gpu
 DT = np.float32(1.0 / 3000.0)
-SCHEDULES = [xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
+SCHEDULES = [xf.SCHEDULE_BRICKS, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
 
 
 def settings_pair(**kw):

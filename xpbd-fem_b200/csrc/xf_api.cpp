@@ -31,6 +31,8 @@ namespace {
 		if (_e != cudaSuccess) { return FailCuda(_e, #call); }       \
 	} while (0)
 
+constexpr uint32_t kBrickSlotCap = 3000; // private vertices per CTA kept in shared memory (96 KB; 2 CTAs per SM)
+
 template <typename T>
 cudaError_t Upload(T** dst, const std::vector<T>& src) {
 	cudaError_t e = cudaMalloc((void**)dst, sizeof(T) * std::max<size_t>(src.size(), 1));
@@ -72,7 +74,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -94,15 +96,28 @@ int UploadScene(xf_scene* s) {
 	XF_CUDA(Upload(&d.O, x0));
 	XF_CUDA(Upload(&d.X0, x0));
 	XF_CUDA(Upload(&d.V, zero));
-	// colour-sorted element planes
-	std::vector<uint32_t> streamToSorted(m.nT);
-	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[m.order[pos]] = pos; }
-	PackedElements pk;
-	PackElements(m, m.order, nullptr, &pk);
+	// element planes: colour-major, brick-minor (one brick per CTA of the persistent grid: 2 CTAs x 256 threads per SM)
+	BrickPlan bp;
+	BuildBricks(m, (uint32_t)(2 * s->smCount), kBrickSlotCap, &bp);
+	std::vector<uint32_t> streamToSorted(m.nT), canonPos(m.nT), serialPos(m.nT);
+	for (uint32_t pos = 0; pos < m.nT; pos++) { serialPos[m.order[pos]] = pos; }
+	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[bp.deviceOrder[pos]] = pos; canonPos[pos] = serialPos[bp.deviceOrder[pos]]; }
+	PackedElements pk, pkb;
+	PackElements(m, bp.deviceOrder, nullptr, &pk);
+	PackElements(m, bp.deviceOrder, bp.encodedIdx.data(), &pkb);
 	XF_CUDA(Upload(&d.eA, pk.a));
 	XF_CUDA(Upload(&d.eB, pk.b));
 	XF_CUDA(Upload(&d.eC, pk.c));
 	XF_CUDA(Upload(&d.eArea, pk.area));
+	XF_CUDA(Upload(&d.eAb, pkb.a));
+	XF_CUDA(Upload(&d.canonPos, canonPos));
+	XF_CUDA(Upload(&d.brickStart, bp.brickStart));
+	XF_CUDA(Upload(&d.privStart, bp.privStart));
+	XF_CUDA(Upload(&d.privVerts, bp.privVerts));
+	XF_CUDA(Upload(&d.sharedVerts, bp.sharedVerts));
+	d.nBricks = bp.nBricks;
+	d.nSharedVerts = (uint32_t)bp.sharedVerts.size();
+	d.maxPrivPerBrick = bp.maxPrivPerBrick;
 	XF_CUDA(Upload(&d.streamToSorted, streamToSorted));
 	XF_CUDA(cudaMalloc((void**)&d.eScratch, sizeof(float) * m.nT));
 	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
@@ -167,7 +182,7 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 	*outScene = nullptr;
 	if (params->abiVersion != XF_ABI_VERSION) { return Fail(XF_ERR_INVALID, "xf_create_params.abiVersion mismatch"); }
 	if (params->precision != XF_PRECISION_EXACT && params->precision != XF_PRECISION_FAST) { return Fail(XF_ERR_INVALID, "bad precision"); }
-	if (params->schedule < XF_SCHEDULE_AUTO || params->schedule > XF_SCHEDULE_PERSISTENT) { return Fail(XF_ERR_INVALID, "bad schedule"); }
+	if (params->schedule < XF_SCHEDULE_AUTO || params->schedule > XF_SCHEDULE_BRICKS) { return Fail(XF_ERR_INVALID, "bad schedule"); }
 	xf_scene* s = new (std::nothrow) xf_scene();
 	if (!s) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
 	std::string err;
@@ -195,10 +210,10 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		}
 		rc = UploadScene(s);
 		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
-		if (s->schedule == XF_SCHEDULE_AUTO) { s->schedule = s->cooperative ? XF_SCHEDULE_PERSISTENT : XF_SCHEDULE_LAUNCH_PER_COLOR; }
-		if (s->schedule == XF_SCHEDULE_PERSISTENT && !s->cooperative) {
+		if (s->schedule == XF_SCHEDULE_AUTO) { s->schedule = s->cooperative ? XF_SCHEDULE_PERSISTENT : XF_SCHEDULE_LAUNCH_PER_COLOR; } // BRICKS measured slower, see xf_bricks.cu
+		if (s->schedule >= XF_SCHEDULE_PERSISTENT && !s->cooperative) {
 			FreeDevice(s); delete s;
-			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT)");
+			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT / XF_SCHEDULE_BRICKS)");
 		}
 	}
 	*outScene = s;
@@ -248,7 +263,9 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 	rc = BuildParams(s, st, manip, dt, &p);
 	if (rc != XF_OK) { return rc; }
 	const bool exact = s->precision == XF_PRECISION_EXACT;
-	if (s->schedule == XF_SCHEDULE_PERSISTENT) {
+	if (s->schedule == XF_SCHEDULE_BRICKS) {
+		XF_CUDA(LaunchSubstepsBricks(s->dev, p, exact, n, s->smCount, s->stream, &s->launches));
+	} else if (s->schedule == XF_SCHEDULE_PERSISTENT) {
 		auto it = s->shapes.find(p.energy);
 		if (it == s->shapes.end()) {
 			LaunchShape shape;
@@ -423,7 +440,10 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 	out->minColorSize = mn;
 	out->maxColorSize = mx;
 	out->smCount = (uint32_t)s->smCount;
-	if (!s->shapes.empty()) {
+	if (s->schedule == XF_SCHEDULE_BRICKS) {
+		out->gridBlocks = s->dev.nBricks;
+		out->blockThreads = 256;
+	} else if (!s->shapes.empty()) {
 		out->gridBlocks = (uint32_t)s->shapes.begin()->second.gridBlocks;
 		out->blockThreads = (uint32_t)s->shapes.begin()->second.blockThreads;
 	}

@@ -57,9 +57,9 @@ __device__ __forceinline__ void LoadConst32B(const void* p, uint32_t (&r)[8]) {
 }
 
 template <bool NEED_PREFACTORED, bool EXACT>
-__device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, ElemRec& r) {
+__device__ __forceinline__ void LoadElementFrom(const ElemRecA* planeA, const DeviceScene& sc, uint32_t e, ElemRec& r) {
 	uint32_t a[8], b[8];
-	LoadConst32B(sc.eA + e, a);
+	LoadConst32B(planeA + e, a);
 	LoadConst32B(sc.eB + e, b);
 	r.idx = make_uint4(a[0], a[1], a[2], a[3]);
 	r.Qi[0][0] = __uint_as_float(a[4]); r.Qi[0][1] = __uint_as_float(a[5]); r.Qi[0][2] = __uint_as_float(a[6]);
@@ -81,6 +81,10 @@ __device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, E
 			r.QR[2] = 2.0f * Op<false>::dot(r.Qi[1], r.Qi[2]);
 		}
 	}
+}
+template <bool NEED_PREFACTORED, bool EXACT>
+__device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, ElemRec& r) {
+	LoadElementFrom<NEED_PREFACTORED, EXACT>(sc.eA, sc, e, r);
 }
 __device__ __forceinline__ uint4 LoadElementIdx(const DeviceScene& sc, uint32_t e) { return __ldg(reinterpret_cast<const uint4*>(sc.eA + e)); }
 
@@ -450,13 +454,11 @@ __device__ __forceinline__ void DeviatoricTerm(const ElemRec& e, const float (&P
 }
 
 // One element of GeoLinear3d::Constrain's main sweep.
+// One element of the main sweep with its four vertex records already in registers (`v` is updated and stored).
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
-__device__ __forceinline__ void SolveElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
+__device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS& p, const ElemRec& e, VertexRegs (&v)[4]) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
-	VertexRegs v[4];
-#pragma unroll
-	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); }
 	float comp0 = O::div(p.invMu, e.volume);
 	float comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, e.volume);
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
@@ -477,6 +479,15 @@ __device__ __forceinline__ void SolveElement(const VS& vs, const PARAMS& p, cons
 	}
 #pragma unroll
 	for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
+__device__ __forceinline__ void SolveElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
+	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
+	VertexRegs v[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); }
+	SolveElementGathered<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, e, v);
 }
 
 // SolveVolumeOnly, Fem.cpp:840-867 (J -> 1 with compliance * volume, never damped).

@@ -7,86 +7,11 @@
 
 #include "xf_element.cuh"
 #include "xf_dispatch.cuh"
+#include "xf_phase.cuh"
 
 namespace xf {
 
 namespace cg = cooperative_groups;
-
-// ------------------------------------------------------------------------------------------------
-// Vertex phases.  post = ground (x1) -> locks -> manipulator -> handles (x2) -> velocity update
-// (Geo.cpp:318-344); predict = Geo.cpp:307-312.  Fused into one pass between substeps when no damping
-// sweep separates them.
-// ------------------------------------------------------------------------------------------------
-template <bool EXACT>
-__device__ __forceinline__ void DragTowards(VertexRegs& v, const float* target, float c18) {
-	typedef Op<EXACT> O;
-	float k = O::div(v.w, O::add(fmaxf(0.000001f, v.w), c18));
-#pragma unroll
-	for (int c = 0; c < 3; c++) {
-		float d = O::mul(O::sub(target[c], __double2float_rn(v.x[c])), k);
-		v.x[c] = O::dadd(v.x[c], (double)d);
-	}
-}
-
-template <bool EXACT>
-__device__ __forceinline__ void VertexPhase(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict) {
-	typedef Op<EXACT> O;
-	VertexRegs v = LoadVertex(sc.Xw, i);
-	double o[3], vel[3];
-	LoadD3(sc.O, i, o);
-	if (doPost) {
-		if (p.groundOn) {
-			double y0 = (double)p.groundY;
-			if (v.x[1] < y0) {
-				double keepT = (double)p.groundKeep;
-				v.x[1] = y0;
-				v.x[0] = O::dadd(o[0], O::dmul(O::dsub(v.x[0], o[0]), keepT));
-				v.x[2] = O::dadd(o[2], O::dmul(O::dsub(v.x[2], o[2]), keepT));
-			}
-		}
-		if (p.lockLeft && (v.flags & XF_VERT_LEFT)) {
-			v.x[0] = o[0]; v.x[1] = o[1]; v.x[2] = o[2];
-			v.w = 0.0f;
-		}
-		if (p.lockRight && (v.flags & XF_VERT_RIGHT)) {
-			double x0d[3];
-			LoadD3(sc.X0, i, x0d);
-			float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
-#pragma unroll
-			for (int r = 0; r < 3; r++) {
-				float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
-				double q = (double)O::add(p.origin[r], t);
-				v.x[r] = q;
-				o[r] = q;
-			}
-			v.w = 0.0f;
-		}
-		if (p.manipOn && i == p.manipIdx) { DragTowards<EXACT>(v, p.manipTarget, p.c18); }
-		for (uint32_t h = 0; h < p.handleCount; h++) {
-			if (p.handleIdx[h] == i) { DragTowards<EXACT>(v, p.handleTarget[h], p.c18); }
-		}
-		double invDt = (double)p.invDt;
-#pragma unroll
-		for (int k = 0; k < 3; k++) { vel[k] = O::dmul(O::dsub(v.x[k], o[k]), invDt); }
-	} else {
-		LoadD3(sc.V, i, vel);
-	}
-	if (doPredict) {
-		double g[3] = { (double)p.gdtX, (double)p.gdtY, 0.0 };
-		double keep = (double)p.keep;
-		double ddt = (double)p.dt;
-#pragma unroll
-		for (int k = 0; k < 3; k++) {
-			vel[k] = O::dadd(vel[k], g[k]);
-			vel[k] = O::dmul(vel[k], keep);
-			o[k] = v.x[k];
-			v.x[k] = O::dadd(v.x[k], O::dmul(vel[k], ddt));
-		}
-	}
-	StoreVertex(sc.Xw, i, v);
-	StoreD3(sc.O, i, o);
-	StoreD3(sc.V, i, vel);
-}
 
 template <bool EXACT>
 __global__ void __launch_bounds__(256) k_vertex_phase(const DeviceScene sc, const __grid_constant__ SubstepParams p, int doPost, int doPredict) {
@@ -120,9 +45,10 @@ __device__ __forceinline__ void SweepOne(const DeviceScene& sc, const SubstepPar
 }
 
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-__global__ void __launch_bounds__(256) k_sweep_color(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t begin, uint32_t end) {
+__global__ void __launch_bounds__(256) k_sweep_color(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t begin, uint32_t end,
+                                                     uint32_t lo, uint32_t hi) {
 	uint32_t e = begin + blockIdx.x * blockDim.x + threadIdx.x;
-	if (e < end) { SweepOne<KIND, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e); }
+	if (e < end && (KIND < 2 || InSlice(sc, e, lo, hi))) { SweepOne<KIND, ENERGY, SIMUL, EXACT, DAMPED>(sc, p, e); }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -145,18 +71,6 @@ __device__ __forceinline__ void GridBarrier(unsigned int* counter, unsigned int&
 		__threadfence();
 	}
 	__syncthreads();
-}
-
-// Amortised damping slice [count*k/8, count*(k+1)/8) of the serial order, Geo.cpp:794-797.
-__device__ __forceinline__ void DampSlice(const SubstepParams& p, uint32_t nT, uint32_t tick, uint32_t& lo, uint32_t& hi) {
-	if (p.rayleigh == XF_RAYLEIGH_POST_AMORTIZED) {
-		uint32_t k = tick % XF_AMORTIZATION_PERIOD;
-		lo = (uint32_t)(((uint64_t)nT * k) / XF_AMORTIZATION_PERIOD);
-		hi = (uint32_t)(((uint64_t)nT * (k + 1)) / XF_AMORTIZATION_PERIOD);
-	} else {
-		lo = 0;
-		hi = nT;
-	}
 }
 
 // One colour range [b, end) swept by the whole grid.  Work is dealt out in warp-sized chunks round-robin over
@@ -226,18 +140,20 @@ __global__ void __launch_bounds__(XF_PERSIST_THREADS, XF_PERSIST_MIN_BLOCKS) k_s
 			DampSlice(p, sc.nT, p.tickId + s, lo, hi);
 			if (p.doDamp) {
 				for (uint32_t c = 0; c < nC; c++) {
-					const uint32_t b = max(p.colorStart[c], lo), end = min(p.colorStart[c + 1], hi);
-					if (b < end) {
-						for (uint32_t e = b + slot; e < end; e += gsize) { SweepOne<2, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+					if (p.colorStart[c] < hi && p.colorStart[c + 1] > lo) {
+						for (uint32_t e = p.colorStart[c] + slot; e < p.colorStart[c + 1]; e += gsize) {
+							if (InSlice(sc, e, lo, hi)) { SweepOne<2, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+						}
 						grid.sync();
 					}
 				}
 			}
 			if (p.doPbdDamp) {
 				for (uint32_t c = 0; c < nC; c++) {
-					const uint32_t b = max(p.colorStart[c], lo), end = min(p.colorStart[c + 1], hi);
-					if (b < end) {
-						for (uint32_t e = b + slot; e < end; e += gsize) { SweepOne<3, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+					if (p.colorStart[c] < hi && p.colorStart[c + 1] > lo) {
+						for (uint32_t e = p.colorStart[c] + slot; e < p.colorStart[c + 1]; e += gsize) {
+							if (InSlice(sc, e, lo, hi)) { SweepOne<3, ENERGY, SIMUL, EXACT, false>(sc, p, e); }
+						}
 						grid.sync();
 					}
 				}
@@ -368,9 +284,9 @@ namespace {
 inline dim3 GridFor(uint32_t n, int threads) { return dim3((n + threads - 1) / threads); }
 
 template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-cudaError_t LaunchSweepT(const DeviceScene& sc, const SubstepParams& p, uint32_t b, uint32_t e, cudaStream_t st) {
+cudaError_t LaunchSweepT(const DeviceScene& sc, const SubstepParams& p, uint32_t b, uint32_t e, cudaStream_t st, uint32_t lo = 0, uint32_t hi = 0xffffffffu) {
 	if (b >= e) { return cudaSuccess; }
-	k_sweep_color<KIND, ENERGY, SIMUL, EXACT, DAMPED><<<GridFor(e - b, 256), 256, 0, st>>>(sc, p, b, e);
+	k_sweep_color<KIND, ENERGY, SIMUL, EXACT, DAMPED><<<GridFor(e - b, 256), 256, 0, st>>>(sc, p, b, e, lo, hi);
 	return cudaGetLastError();
 }
 
@@ -403,16 +319,19 @@ struct PerColorRunner {
 					lo = (uint32_t)(((uint64_t)sc.nT * k) / XF_AMORTIZATION_PERIOD);
 					hi = (uint32_t)(((uint64_t)sc.nT * (k + 1)) / XF_AMORTIZATION_PERIOD);
 				}
+				// the serial order is colour-major too: colour c intersects the slice iff the ranges overlap
 				if (p.doDamp) {
 					for (uint32_t c = 0; c < p.nColors; c++) {
-						uint32_t b = p.colorStart[c] > lo ? p.colorStart[c] : lo, e = p.colorStart[c + 1] < hi ? p.colorStart[c + 1] : hi;
-						if (b < e) { ok(LaunchSweepT<2, ENERGY, SIMUL, EXACT, false>(sc, p, b, e, st)); ++*launches; }
+						if (p.colorStart[c] < hi && p.colorStart[c + 1] > lo) {
+							ok(LaunchSweepT<2, ENERGY, SIMUL, EXACT, false>(sc, p, p.colorStart[c], p.colorStart[c + 1], st, lo, hi)); ++*launches;
+						}
 					}
 				}
 				if (p.doPbdDamp) {
 					for (uint32_t c = 0; c < p.nColors; c++) {
-						uint32_t b = p.colorStart[c] > lo ? p.colorStart[c] : lo, e = p.colorStart[c + 1] < hi ? p.colorStart[c + 1] : hi;
-						if (b < e) { ok(LaunchSweepT<3, ENERGY, SIMUL, EXACT, false>(sc, p, b, e, st)); ++*launches; }
+						if (p.colorStart[c] < hi && p.colorStart[c + 1] > lo) {
+							ok(LaunchSweepT<3, ENERGY, SIMUL, EXACT, false>(sc, p, p.colorStart[c], p.colorStart[c + 1], st, lo, hi)); ++*launches;
+						}
 					}
 				}
 			}
