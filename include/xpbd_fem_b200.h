@@ -196,6 +196,21 @@ typedef struct xf_info {
 } xf_info;
 int xf_get_info(const xf_scene* scene, xf_info* out);
 
+/* ---- frame driver: Sim::Update (Demo.cpp:37-103) for one Geo ----
+ * Per frame: substep count from the wall-clock dt (clamped to ceil(medianFrameTime / sdt)), the time-corrected
+ * PBD-damping / drag constants written into *settings like the reference does, the right-side lock transform and the
+ * manipulator ray animated with substep resolution, tickId advanced.  xf_frame_state holds Sim's persistent scalars
+ * (Demo.h:40-44). */
+typedef struct xf_frame_state {
+	float dtResidual;
+	uint32_t tickId;
+	float leftRightSeparationOld;
+	float rightRotationTheta;
+} xf_frame_state;
+void xf_frame_state_init(xf_frame_state* state);
+int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipulator* manip, float dt, float medianFrameTime, xf_frame_state* state,
+                    uint32_t* outSubsteps);
+
 /* ---- batched scenes (BASELINE config 3): nScenes independent instances of ONE rest mesh, each with its own
  * state and Settings, e.g. a vector of RL environments.  The reference would hold them as nScenes Geo objects and
  * call Geo::Substep on each (Sim::Update's `for geo` loop, Demo.cpp:86-88); here one call steps all of them, one

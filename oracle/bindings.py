@@ -440,6 +440,51 @@ class OracleScene:
         return float(self.lib.xo_time_substeps(self.h, C.byref(settings), dt, n))
 
 
+class RefSim:
+    """The reference's own Sim (Demo.h:18-52) holding one T4 block, stepped by Sim::Update."""
+
+    def __init__(self, nodes, idx_stream, settings, auto_resize=False, kind="strict"):
+        lib = _load_ref(kind)
+        vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
+        lib.ref_sim_create.restype = vp
+        lib.ref_sim_create.argtypes = [vp, u32, vp, u32, vp, C.c_int]
+        lib.ref_sim_destroy.argtypes = [vp]
+        lib.ref_sim_set_order.argtypes = [vp, vp]
+        lib.ref_sim_get_state.argtypes = [vp, vp, vp, vp]
+        lib.ref_sim_update.restype = u32
+        lib.ref_sim_update.argtypes = [vp, vp, vp, f32, f32]
+        self.lib = lib
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        self.nV = nodes.size // 3
+        self.h = C.c_void_p(lib.ref_sim_create(_vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, C.byref(settings), 1 if auto_resize else 0))
+
+    def close(self):
+        if self.h:
+            self.lib.ref_sim_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_order(self, order):
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        self.lib.ref_sim_set_order(self.h, _vp(order))
+
+    def update(self, settings, dt, median_frame_time, manip=None):
+        return self.lib.ref_sim_update(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, dt, median_frame_time)
+
+    def get_state(self):
+        X = np.empty((self.nV, 3), dtype=np.float64)
+        V = np.empty((self.nV, 3), dtype=np.float64)
+        w = np.empty(self.nV, dtype=np.float32)
+        self.lib.ref_sim_get_state(self.h, _vp(X), _vp(V), _vp(w))
+        return X, V, w
+
+
 # ---------------------------------------------------------------------------------------------
 # The product's reference-side adapter (GeoLinear3dCuda : Geo) hosted by the reference harness
 # ---------------------------------------------------------------------------------------------

@@ -21,6 +21,7 @@
 // monolithic; with both extensions disabled ref_substep_ext is checked bit-for-bit against
 // Geo3d::Substep by tests/test_oracle_ref.py.  Parity for the extensions themselves is
 // "unpinned" by the reference.
+#include "Demo.h"
 #include "Geo.h"
 #include "MeshGen.h"
 
@@ -28,6 +29,8 @@
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+
+extern "C" double performance_now() { return 0.0; } // Demo.cpp:14 (only feeds the HUD averages)
 
 namespace {
 
@@ -355,6 +358,51 @@ void ref_adapter_get_state(void* h, double* X, double* V, float* w) {
 	if (w) { memcpy(w, a->impl->hostW.data(), sizeof(float) * n); }
 }
 #endif
+
+// ---- the reference's own frame driver: Sim (Demo.h:18-52) with one T4 block, stepped by Sim::Update ----
+struct RefSim {
+	Sim* sim = nullptr;
+	Manipulator manip;
+};
+void* ref_sim_create(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, const void* settings160, int autoResize) {
+	RefSim* r = new RefSim();
+	r->sim = new Sim();
+	r->sim->Reset();
+	memcpy((void*)&r->sim->settings, settings160, sizeof(Settings));
+	r->sim->AddBlock(Element_T4, nodeXYZ, nodeFloatCount, idxStream, idxCount, autoResize != 0);
+	r->sim->FinishAddingBlocks(); // Transform (rotate / offset) + volume0, Demo.cpp:156-168
+	r->manip = ToManip(nullptr, nullptr);
+	return r;
+}
+void ref_sim_destroy(void* h) { RefSim* r = (RefSim*)h; if (r) { delete r->sim; delete r; } }
+void ref_sim_set_order(void* h, const uint32_t* order) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefSim*)h)->sim->geos[0];
+	memcpy(g->tOrder, order, sizeof(uint32_t) * g->con.tetCount);
+}
+void ref_sim_get_state(void* h, double* X, double* V, float* w) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefSim*)h)->sim->geos[0];
+	for (uint32_t i = 0; i < g->vertCount; i++) {
+		if (X) { X[3 * i + 0] = g->X[i].x; X[3 * i + 1] = g->X[i].y; X[3 * i + 2] = g->X[i].z; }
+		if (V) { V[3 * i + 0] = g->V[i].x; V[3 * i + 1] = g->V[i].y; V[3 * i + 2] = g->V[i].z; }
+		if (w) { w[i] = g->w[i]; }
+	}
+}
+// One Sim::Update.  settings160 / manipPod are in-out like the reference's members; returns the tick advance (= substeps).
+uint32_t ref_sim_update(void* h, void* settings160, void* manipPod, float dt, float medianFrameTime) {
+	RefSim* r = (RefSim*)h;
+	Sim* sim = r->sim;
+	// the UI writes sim.settings every frame (Demo::UpdateSettings, Demo.cpp:342); keep Sim's auto-updated members
+	Settings in;
+	memcpy((void*)&in, settings160, sizeof(Settings));
+	sim->settings = in;
+	ManipPod* mp = (ManipPod*)manipPod;
+	Manipulator manip = ToManip(mp, sim->geos[0]);
+	const uint32_t tick0 = sim->tickId;
+	sim->Update(dt, medianFrameTime, &manip);
+	memcpy(settings160, (void*)&sim->settings, sizeof(Settings));
+	if (mp) { mp->pickDirTarget[0] = manip.pickDirTarget.x; mp->pickDirTarget[1] = manip.pickDirTarget.y; mp->pickDirTarget[2] = manip.pickDirTarget.z; }
+	return sim->tickId - tick0;
+}
 
 // Timing leg for bench.py: run `n` reference substeps and return elapsed seconds.
 double ref_time_substeps(void* h, const void* settings160, float dt, uint32_t n) {

@@ -71,12 +71,23 @@ class CreateParams(C.Structure):
     ]
 
 
+class FrameState(C.Structure):
+    """Sim's persistent per-simulation scalars (Demo.h:40-44)."""
+    _fields_ = [("dtResidual", C.c_float), ("tickId", C.c_uint32), ("leftRightSeparationOld", C.c_float), ("rightRotationTheta", C.c_float)]
+
+
 class Info(C.Structure):
     _fields_ = [
         ("vertCount", C.c_uint32), ("elementCount", C.c_uint32), ("colorCount", C.c_uint32), ("minColorSize", C.c_uint32),
         ("maxColorSize", C.c_uint32), ("smCount", C.c_uint32), ("gridBlocks", C.c_uint32), ("blockThreads", C.c_uint32),
         ("elementRecordBytes", C.c_uint32), ("schedule", C.c_uint32), ("kernelLaunches", C.c_uint64), ("l2Bytes", C.c_uint64),
     ]
+
+
+def new_frame_state():
+    st = FrameState()
+    lib().xf_frame_state_init(C.byref(st))
+    return st
 
 
 def make_settings(energy=Energy_MixedSel, simultaneous=True, poisson=0.5, compliance=1.0, gravity=(0.0, -0.4905), damping=0.0,
@@ -109,6 +120,7 @@ EXPORTS = [
     "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_elements", "xf_substep",
     "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
+    "xf_frame_state_init", "xf_frame_update",
     "xf_batch_create", "xf_batch_destroy", "xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count",
     "xf_batch_color_count", "xf_batch_get_order", "xf_batch_set_ground", "xf_batch_substep", "xf_batch_sync",
     "xf_batch_get_state", "xf_batch_set_state", "xf_batch_get_info",
@@ -156,6 +168,9 @@ def lib():
     L.xf_volume.argtypes = [vp, C.POINTER(f32)]
     L.xf_stats.argtypes = [vp, vp, vp]
     L.xf_get_info.argtypes = [vp, C.POINTER(Info)]
+    L.xf_frame_state_init.argtypes = [C.POINTER(FrameState)]
+    L.xf_frame_state_init.restype = None
+    L.xf_frame_update.argtypes = [vp, vp, vp, f32, f32, C.POINTER(FrameState), C.POINTER(u32)]
     L.xf_batch_create.argtypes = [C.POINTER(CreateParams), vp, u32, vp, u32, u32, C.POINTER(vp)]
     L.xf_batch_destroy.argtypes = [vp]
     for n in ("xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count", "xf_batch_color_count"):
@@ -287,6 +302,13 @@ class GeoLinear3dCuda:
         v = C.c_float()
         _check(lib().xf_volume(self._h, C.byref(v)))
         return float(v.value)
+
+    def FrameUpdate(self, settings, dt, median_frame_time, state, manip=None):
+        """Sim::Update for this geo (Demo.cpp:37-103); returns the number of substeps taken."""
+        n = C.c_uint32()
+        _check(lib().xf_frame_update(self._h, C.byref(settings), C.byref(manip) if manip is not None else None, float(dt),
+                                     float(median_frame_time), C.byref(state), C.byref(n)))
+        return n.value
 
     # ---- public members of the reference's Geo3d / GeoLinear3d ------------------------------------
     def get_order(self):
