@@ -71,7 +71,8 @@ def gpu_count():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("extra", [[], ["--serial", "--energy", "4", "--poisson", "0.4999"], ["--no-hint", "--energy", "5"]])
+@pytest.mark.parametrize("extra", [[], ["--serial", "--energy", "4", "--poisson", "0.4999"], ["--no-hint", "--energy", "5"],
+                                   ["--schedule", "persistent"], ["--schedule", "persistent", "--energy", "3", "--poisson", "0.45"]])
 def test_partitioned_gpu_matches_oracle(extra):
     if gpu_count() < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")

@@ -26,6 +26,7 @@ ap.add_argument("--substeps", type=int, default=12)
 ap.add_argument("--no-hint", action="store_true")
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--time-substeps", type=int, default=0)
+ap.add_argument("--schedule", choices=["persistent", "per_color"], default="per_color")
 a = ap.parse_args()
 xf = load_package()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -91,7 +92,8 @@ if a.mode == "emulate":
 else:
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint)
+    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint,
+                               schedule=xf.SCHEDULE_PERSISTENT if a.schedule == "persistent" else xf.SCHEDULE_LAUNCH_PER_COLOR)
     blob = torch.from_numpy(part.ipc_export()).cuda()
     allb = [torch.empty_like(blob) for _ in range(world)]
     dist.all_gather(allb, blob)
@@ -129,7 +131,7 @@ if rank == 0:
             if not (np.array_equal(Xr, Xo[g]) and np.array_equal(Vr, Vo[g]) and np.array_equal(wr, wo[g])):
                 ok = False
                 msg = "rank %d differs: max|dX| = %.3e" % (r, np.abs(Xr - Xo[g]).max())
-    out = {"mode": a.mode, "world": world, "tets": int(idx.size // 5), "verts": int(nVg), "ok": ok, "msg": msg,
+    out = {"mode": a.mode, "schedule": a.schedule, "world": world, "tets": int(idx.size // 5), "verts": int(nVg), "ok": ok, "msg": msg,
            "shared_verts_rank0": int(sum(len(part.halo(c, s, True)) for c in range(part.nColors) for s in range(part.nPeers)))}
     if a.mode == "gpu" and a.time_substeps:
         out["us_per_substep"] = 1e6 * timing / a.time_substeps

@@ -465,7 +465,7 @@ class GeoPartitionCuda:
     IPC_BYTES = 128
 
     def __init__(self, nodes, idx_stream, n_ranks, rank, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
-                 color_hint=None, stream=None):
+                 color_hint=None, stream=None, schedule=SCHEDULE_AUTO):
         L = lib()
         nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
         idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
@@ -475,6 +475,7 @@ class GeoPartitionCuda:
         p.density = density
         p.autoResize = 1 if auto_resize else 0
         p.precision = precision
+        p.schedule = schedule
         p.stream = stream
         if color_hint is not None:
             color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)

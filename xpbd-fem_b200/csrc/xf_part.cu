@@ -10,6 +10,8 @@
 // the global colour order needs.  NCCL/torch.distributed (or anything else) is only needed to move the 128-byte
 // IPC handles at start-up.  Spin loops carry a bail-out so a protocol error reports XF_ERR_CUDA instead of
 // hanging the GPU.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cstring>
 #include <new>
@@ -36,6 +38,9 @@ struct PartDevice {
 	const uint32_t* shareRemoteIdx;
 	unsigned int* doneCounter;
 	unsigned int* errorFlag;
+	const uint32_t* colorStart;   // device copies for the persistent kernel
+	const uint32_t* ifaceEnd;
+	uint32_t nColors;
 };
 
 __device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
@@ -109,64 +114,164 @@ __global__ void __launch_bounds__(256) k_part_sweep(const __grid_constant__ Part
 
 // vertex phase of the partitioned run: identical arithmetic to k_vertex_phase, on every local copy
 template <bool EXACT>
+__device__ __forceinline__ void PartVertexPhaseOne(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict) {
+	typedef Op<EXACT> O;
+	VertexRegs v = LoadVertex(sc.Xw, i);
+	double o[3], vel[3];
+	LoadD3(sc.O, i, o);
+	if (doPost) {
+		if (p.groundOn) {
+			double y0 = (double)p.groundY;
+			if (v.x[1] < y0) {
+				double keepT = (double)p.groundKeep;
+				v.x[1] = y0;
+				v.x[0] = O::dadd(o[0], O::dmul(O::dsub(v.x[0], o[0]), keepT));
+				v.x[2] = O::dadd(o[2], O::dmul(O::dsub(v.x[2], o[2]), keepT));
+			}
+		}
+		if (p.lockLeft && (v.flags & XF_VERT_LEFT)) { v.x[0] = o[0]; v.x[1] = o[1]; v.x[2] = o[2]; v.w = 0.0f; }
+		if (p.lockRight && (v.flags & XF_VERT_RIGHT)) {
+			double x0d[3];
+			LoadD3(sc.X0, i, x0d);
+			float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
+#pragma unroll
+			for (int r = 0; r < 3; r++) {
+				float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
+				double q = (double)O::add(p.origin[r], t);
+				v.x[r] = q;
+				o[r] = q;
+			}
+			v.w = 0.0f;
+		}
+		double invDt = (double)p.invDt;
+#pragma unroll
+		for (int k = 0; k < 3; k++) { vel[k] = O::dmul(O::dsub(v.x[k], o[k]), invDt); }
+	} else {
+		LoadD3(sc.V, i, vel);
+	}
+	if (doPredict) {
+		double g[3] = { (double)p.gdtX, (double)p.gdtY, 0.0 };
+		double keep = (double)p.keep;
+		double ddt = (double)p.dt;
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			vel[k] = O::dadd(vel[k], g[k]);
+			vel[k] = O::dmul(vel[k], keep);
+			o[k] = v.x[k];
+			v.x[k] = O::dadd(v.x[k], O::dmul(vel[k], ddt));
+		}
+	}
+	StoreVertex(sc.Xw, i, v);
+	StoreD3(sc.O, i, o);
+	StoreD3(sc.V, i, vel);
+}
+
+// vertex phase of the partitioned run: identical arithmetic to k_vertex_phase, on every local copy
+template <bool EXACT>
 __global__ void __launch_bounds__(256) k_part_vertex_phase(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, int doPost,
                                                            int doPredict, unsigned long long epoch) {
-	typedef Op<EXACT> O;
 	PhaseWait(pd, epoch);
-	const DeviceScene& sc = pd.local;
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < sc.nV) {
-		VertexRegs v = LoadVertex(sc.Xw, i);
-		double o[3], vel[3];
-		LoadD3(sc.O, i, o);
-		if (doPost) {
-			if (p.groundOn) {
-				double y0 = (double)p.groundY;
-				if (v.x[1] < y0) {
-					double keepT = (double)p.groundKeep;
-					v.x[1] = y0;
-					v.x[0] = O::dadd(o[0], O::dmul(O::dsub(v.x[0], o[0]), keepT));
-					v.x[2] = O::dadd(o[2], O::dmul(O::dsub(v.x[2], o[2]), keepT));
-				}
-			}
-			if (p.lockLeft && (v.flags & XF_VERT_LEFT)) { v.x[0] = o[0]; v.x[1] = o[1]; v.x[2] = o[2]; v.w = 0.0f; }
-			if (p.lockRight && (v.flags & XF_VERT_RIGHT)) {
-				double x0d[3];
-				LoadD3(sc.X0, i, x0d);
-				float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
-#pragma unroll
-				for (int r = 0; r < 3; r++) {
-					float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
-					double q = (double)O::add(p.origin[r], t);
-					v.x[r] = q;
-					o[r] = q;
-				}
-				v.w = 0.0f;
-			}
-			double invDt = (double)p.invDt;
-#pragma unroll
-			for (int k = 0; k < 3; k++) { vel[k] = O::dmul(O::dsub(v.x[k], o[k]), invDt); }
-		} else {
-			LoadD3(sc.V, i, vel);
-		}
-		if (doPredict) {
-			double g[3] = { (double)p.gdtX, (double)p.gdtY, 0.0 };
-			double keep = (double)p.keep;
-			double ddt = (double)p.dt;
-#pragma unroll
-			for (int k = 0; k < 3; k++) {
-				vel[k] = O::dadd(vel[k], g[k]);
-				vel[k] = O::dmul(vel[k], keep);
-				o[k] = v.x[k];
-				v.x[k] = O::dadd(v.x[k], O::dmul(vel[k], ddt));
-			}
-		}
-		StoreVertex(sc.Xw, i, v);
-		StoreD3(sc.O, i, o);
-		StoreD3(sc.V, i, vel);
-	}
+	if (i < pd.local.nV) { PartVertexPhaseOne<EXACT>(pd.local, p, i, doPost != 0, doPredict != 0); }
 	PhaseSignal(pd, epoch);
 }
+
+// ---- persistent variant: one cooperative launch per xf_part_substep call --------------------------------------
+// Per phase: wait for the peers' previous phase -> interface elements (their new positions are also stored into
+// the peers' copies) -> the last CTA to finish them signals the peers -> interior elements run while the signal
+// crosses NVLink -> local grid barrier.  A peer that sees the signal may already write this rank's shared vertices
+// for the next phase: safe, because only interior elements (private vertices) are still running here.
+__device__ __forceinline__ void SignalPeers(const PartDevice& pd, unsigned long long epoch) {
+	__threadfence_system();
+	for (uint32_t s = 0; s < pd.nPeers; s++) { StoreReleaseSys(pd.peerFlags[s] + pd.myRank, epoch); }
+}
+// Peer wait by ONE thread of the grid, placed right before it joins the local grid barrier: the barrier's release then
+// also means "every peer has finished the interface part of this phase", nobody else polls, and the NVLink latency
+// overlaps the interior elements and the barrier itself.
+__device__ __forceinline__ void PeerWaitSingle(const PartDevice& pd, unsigned long long epoch) {
+	for (uint32_t s = 0; s < pd.nPeers; s++) {
+		const unsigned long long* f = pd.myFlags + pd.peerRank[s];
+		unsigned long long spins = 0, v;
+		do {
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+			if (++spins > (1ull << 27)) { atomicExch(pd.errorFlag, 1u); break; }
+		} while (v < epoch);
+	}
+	asm volatile("fence.acq_rel.sys;" ::: "memory");
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__global__ void __launch_bounds__(256, 2) k_part_persistent(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
+                                                            unsigned long long epoch) {
+	namespace cg = cooperative_groups;
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	cg::grid_group grid = cg::this_grid();
+	const DeviceScene& sc = pd.local;
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+	const uint32_t slot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
+	const MirroredStore mirrored{ StoreOf(sc), &pd };
+	const GlobalStore plain = StoreOf(sc);
+	const bool leader = blockIdx.x == 0 && threadIdx.x == 0;
+	// the previous launch ended with a vertex phase whose epoch the peers may not have reached yet
+	if (leader) { PeerWaitSingle(pd, epoch); }
+	grid.sync();
+	for (uint32_t s = 0; s <= nSubsteps; s++) {
+		// vertex phase (post of substep s-1, predict of substep s); the last iteration is the closing post only.
+		// It touches every local vertex, so the peers are told only after the whole grid has finished it.
+		++epoch;
+		const bool doPost = s > 0, doPredict = s < nSubsteps;
+		for (uint32_t i = gtid; i < sc.nV; i += gsize) { PartVertexPhaseOne<EXACT>(sc, p, i, doPost, doPredict); }
+		grid.sync();
+		if (leader) { SignalPeers(pd, epoch); PeerWaitSingle(pd, epoch); }
+		grid.sync();
+		if (s == nSubsteps) { break; }
+		for (uint32_t c = 0; c < pd.nColors; c++) {
+			++epoch;
+			const uint32_t b = __ldg(pd.colorStart + c), mid = __ldg(pd.ifaceEnd + c), end = __ldg(pd.colorStart + c + 1);
+			bool wroteRemote = false;
+			for (uint32_t e = b + slot; e < mid; e += gsize) {
+				ElemRec rec;
+				LoadElement<kPrefactored, EXACT>(sc, e, rec);
+				SolveElement<ENERGY, SIMUL, EXACT, false>(mirrored, p, rec);
+				wroteRemote = true;
+			}
+			if (__syncthreads_or(wroteRemote ? 1 : 0)) { if (threadIdx.x == 0) { __threadfence_system(); } }
+			if (threadIdx.x == 0) {
+				if (atomicAdd(pd.doneCounter, 1u) == gridDim.x - 1) {
+					*pd.doneCounter = 0;
+					SignalPeers(pd, epoch);
+				}
+			}
+			for (uint32_t e = mid + slot; e < end; e += gsize) {
+				ElemRec rec;
+				LoadElement<kPrefactored, EXACT>(sc, e, rec);
+				SolveElement<ENERGY, SIMUL, EXACT, false>(plain, p, rec);
+			}
+			if (leader) { PeerWaitSingle(pd, epoch); }
+			grid.sync();
+		}
+	}
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct PartPersistentRunner {
+	static cudaError_t Run(const PartDevice& pd, const SubstepParams& p, uint32_t nSubsteps, unsigned long long* epoch, int smCount, cudaStream_t st,
+	                       uint64_t* launches) {
+		if (DAMPED) { return cudaErrorNotSupported; }
+		auto fn = k_part_persistent<ENERGY, SIMUL, EXACT, false>;
+		int perSm = 0;
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, 0);
+		if (e != cudaSuccess) { return e; }
+		if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		const dim3 grid((unsigned)(std::min(perSm, 2) * smCount));
+		unsigned long long epoch0 = *epoch;
+		void* args[] = { (void*)&pd, (void*)&p, (void*)&nSubsteps, (void*)&epoch0 };
+		e = cudaLaunchCooperativeKernel((const void*)fn, grid, dim3(256), args, 0, st);
+		*epoch += (unsigned long long)nSubsteps * (pd.nColors + 1) + 1; // one epoch per vertex phase and per colour
+		++*launches;
+		return e;
+	}
+};
 
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 struct PartRunner {
@@ -212,6 +317,10 @@ struct xf_partition {
 	uint64_t launches = 0;
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
+	int schedule = XF_SCHEDULE_AUTO;
+	int smCount = 0;
+	uint32_t* dColorStart = nullptr;
+	uint32_t* dIfaceEnd = nullptr;
 	uint32_t* dShareStart = nullptr;
 	uint32_t* dShareSlot = nullptr;
 	uint32_t* dShareRemote = nullptr;
@@ -282,6 +391,11 @@ int UploadPart(xf_partition* P) {
 	XFP_CUDA(cudaMalloc((void**)&P->dPackX, sizeof(double) * 3 * std::max(nV, 1u)));
 	XFP_CUDA(cudaMalloc((void**)&P->dPackV, sizeof(double) * 3 * std::max(nV, 1u)));
 	XFP_CUDA(cudaMalloc((void**)&P->dPackW, sizeof(float) * std::max(nV, 1u)));
+	XFP_CUDA(UploadVecP(&P->dColorStart, pl.colorStart));
+	XFP_CUDA(UploadVecP(&P->dIfaceEnd, pl.ifaceEnd));
+	P->dev.colorStart = P->dColorStart;
+	P->dev.ifaceEnd = P->dIfaceEnd;
+	P->dev.nColors = (uint32_t)pl.colorStart.size() - 1;
 	P->dev.nPeers = (uint32_t)pl.peers.size();
 	P->dev.myRank = pl.rank;
 	for (size_t s = 0; s < pl.peers.size(); s++) { P->dev.peerRank[s] = pl.peers[s]; }
@@ -310,6 +424,16 @@ int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_
 	if (P->device >= 0) {
 		cudaError_t e = cudaSetDevice(P->device);
 		if (e != cudaSuccess) { delete P; return FailCuda(e, "cudaSetDevice"); }
+		cudaDeviceProp prop;
+		e = cudaGetDeviceProperties(&prop, P->device);
+		if (e != cudaSuccess) { delete P; return FailCuda(e, "cudaGetDeviceProperties"); }
+		P->smCount = prop.multiProcessorCount;
+		P->schedule = params->schedule;
+		// Measured on 2 x B200 (998 250 tets): launch-per-phase 312 us/substep, persistent 390-426 us/substep; both are
+		// bound by the cross-GPU release/acquire chain (system fence round trip + flag flight, ~10 us per phase), and the
+		// back-to-back launches overlap it slightly better.  AUTO therefore means one launch per phase here.
+		if (P->schedule == XF_SCHEDULE_AUTO || P->schedule == XF_SCHEDULE_BRICKS) { P->schedule = XF_SCHEDULE_LAUNCH_PER_COLOR; }
+		if (P->schedule == XF_SCHEDULE_PERSISTENT && !prop.cooperativeLaunch) { P->schedule = XF_SCHEDULE_LAUNCH_PER_COLOR; }
 		if (params->stream) { P->stream = (cudaStream_t)params->stream; }
 		else {
 			e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
@@ -331,7 +455,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
@@ -450,8 +574,13 @@ int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n
 	p.groundY = P->groundY;
 	p.groundKeep = 1.0f - P->groundFriction;
 	p.handleCount = 0;
-	XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, P->plan.colorStart,
-	                                    P->plan.ifaceEnd, n, &P->epoch, P->stream, &P->launches));
+	if (P->schedule == XF_SCHEDULE_PERSISTENT) {
+		XFP_CUDA(DispatchConfig<PartPersistentRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, n, &P->epoch,
+		                                              P->smCount, P->stream, &P->launches));
+	} else {
+		XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, P->plan.colorStart,
+		                                    P->plan.ifaceEnd, n, &P->epoch, P->stream, &P->launches));
+	}
 	return XF_OK;
 }
 
