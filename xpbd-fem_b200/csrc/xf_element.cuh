@@ -66,21 +66,13 @@ __device__ __forceinline__ void LoadElementFrom(const ElemRecA* planeA, const De
 	r.Qi[1][0] = __uint_as_float(a[7]); r.Qi[1][1] = __uint_as_float(b[0]); r.Qi[1][2] = __uint_as_float(b[1]);
 	r.Qi[2][0] = __uint_as_float(b[2]); r.Qi[2][1] = __uint_as_float(b[3]); r.Qi[2][2] = __uint_as_float(b[4]);
 	r.volume = __uint_as_float(b[5]);
-	if (NEED_PREFACTORED) {
-		if (EXACT) {
-			float4 q = __ldg(sc.eC + e);
-			r.QQ[0] = __uint_as_float(b[6]); r.QQ[1] = __uint_as_float(b[7]); r.QQ[2] = q.x;
-			r.QR[0] = q.y; r.QR[1] = q.z; r.QR[2] = q.w;
-		} else {
-			// QQ_i = |col_i(Qi)|^2, QR = 2 col_i . col_j  (what Fem.cpp:131-161 integrates, up to rounding)
-			r.QQ[0] = Op<false>::dot(r.Qi[0], r.Qi[0]);
-			r.QQ[1] = Op<false>::dot(r.Qi[1], r.Qi[1]);
-			r.QQ[2] = Op<false>::dot(r.Qi[2], r.Qi[2]);
-			r.QR[0] = 2.0f * Op<false>::dot(r.Qi[0], r.Qi[1]);
-			r.QR[1] = 2.0f * Op<false>::dot(r.Qi[0], r.Qi[2]);
-			r.QR[2] = 2.0f * Op<false>::dot(r.Qi[1], r.Qi[2]);
-		}
+	if (NEED_PREFACTORED && EXACT) {
+		float4 q = __ldg(sc.eC + e);
+		r.QQ[0] = __uint_as_float(b[6]); r.QQ[1] = __uint_as_float(b[7]); r.QQ[2] = q.x;
+		r.QR[0] = q.y; r.QR[1] = q.z; r.QR[2] = q.w;
 	}
+	// FAST recomputes QQ/QR from Qi at the point of use (PrefactoredI1): doing it here would make the prefetching
+	// thread wait for the record before it reaches the barrier and serialise the HBM latency into every phase.
 }
 template <bool NEED_PREFACTORED, bool EXACT>
 __device__ __forceinline__ void LoadElement(const DeviceScene& sc, uint32_t e, ElemRec& r) {
@@ -228,8 +220,18 @@ __device__ __forceinline__ float VolumetricFromF(const ElemRec& e, const float (
 
 // Prefactored I1 and gradient.  Fem.cpp:163-192
 template <bool EXACT>
-__device__ __forceinline__ float PrefactoredI1(const ElemRec& e, const float (&P)[3][3], float (&g)[4][3]) {
+__device__ __forceinline__ float PrefactoredI1(const ElemRec& eIn, const float (&P)[3][3], float (&g)[4][3]) {
 	typedef Op<EXACT> O;
+	ElemRec e = eIn;
+	if (!EXACT) {
+		// QQ_i = |col_i(Qi)|^2, QR = 2 col_i . col_j  (what Fem.cpp:131-161 integrates, up to rounding)
+		e.QQ[0] = Op<false>::dot(e.Qi[0], e.Qi[0]);
+		e.QQ[1] = Op<false>::dot(e.Qi[1], e.Qi[1]);
+		e.QQ[2] = Op<false>::dot(e.Qi[2], e.Qi[2]);
+		e.QR[0] = 2.0f * Op<false>::dot(e.Qi[0], e.Qi[1]);
+		e.QR[1] = 2.0f * Op<false>::dot(e.Qi[0], e.Qi[2]);
+		e.QR[2] = 2.0f * Op<false>::dot(e.Qi[1], e.Qi[2]);
+	}
 	float U = 0.0f;
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
