@@ -115,7 +115,7 @@ typedef enum xf_precision {
 
 typedef enum xf_schedule {
 	XF_SCHEDULE_AUTO = 0,
-	XF_SCHEDULE_LAUNCH_PER_COLOR = 1, /* one kernel launch per colour (CUDA-graph replayed) */
+	XF_SCHEDULE_LAUNCH_PER_COLOR = 1, /* one kernel launch per colour phase */
 	XF_SCHEDULE_PERSISTENT = 2,       /* one cooperative launch per xf_substep call, grid barriers between colours */
 	XF_SCHEDULE_BRICKS = 3            /* PERSISTENT + vertices private to a CTA's brick of elements kept in shared memory */
 } xf_schedule;
