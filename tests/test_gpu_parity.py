@@ -225,3 +225,43 @@ def test_device_stats_match_oracle():
     assert abs(s["deviatoric"] - ed) <= 1e-6 * abs(ed) + 1e-12
     assert abs(s["volumetric"] - ev) <= 1e-6 * abs(ev) + 1e-12
     assert abs(s["volume"] - orc.volume()) <= 1e-5 * orc.volume()
+
+
+@pytest.mark.parametrize("dims", [(1, 1), (12, 1), (2, 1)])
+def test_exact_degenerate_shapes(dims):
+    """Shape_Single (one hex = 6 tets) and Shape_Line (12x1x1), Demo.cpp:290-291: fewer elements than threads in a warp,
+    colours with a single element, vertices of low valence."""
+    geo, orc = make_pair(dims[0], dims[1], 0.1)
+    assert geo.nT == 6 * dims[0] * dims[1] * dims[1]
+    st, ost = settings_pair(energy=xf.Energy_YeohSkin, simultaneous=False, poisson=0.5, lock_left=False)
+    geo.Substep(st, DT, 25)
+    orc.substep(ost, DT, 25)
+    assert_bit_exact(geo, orc)
+
+
+def test_zero_substeps_and_empty_mesh():
+    geo, orc = make_pair(3, 2, 0.0)
+    geo.Substep(xf.make_settings(), DT, 0)  # n == 0 is a no-op
+    assert_bit_exact(geo, orc)
+    nodes, idx, _ = xf.GenerateTetBlock(2, 2)
+    with pytest.raises(xf.XfError) as e:
+        xf.GeoLinear3dCuda(nodes, idx[:0])
+    assert e.value.status == xf.XF_ERR_INVALID
+
+
+def test_async_state_transfers_roundtrip():
+    """xf_set_state_async / xf_get_state_async (the per-frame e2e path of bench.py) against the synchronous getters."""
+    geo, orc = make_pair(5, 3, 0.2)
+    st, ost = settings_pair(energy=xf.Energy_MixedSel, poisson=0.495)
+    orc.substep(ost, DT, 15)
+    Xo, Vo, wo = orc.get_state()
+    geo.set_state(w=wo)
+    hX, hV = np.ascontiguousarray(Xo), np.ascontiguousarray(Vo)
+    geo.set_state_async(hX.ctypes.data, hV.ctypes.data)
+    geo.Substep(st, DT, 4)
+    oX, oV = np.empty_like(hX), np.empty_like(hV)
+    geo.get_state_async(oX.ctypes.data, oV.ctypes.data)
+    geo.Sync()
+    orc.substep(ost, DT, 4)
+    Xr, Vr, _ = orc.get_state()
+    assert np.array_equal(oX, Xr) and np.array_equal(oV, Vr)

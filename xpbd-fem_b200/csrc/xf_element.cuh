@@ -29,6 +29,8 @@ struct Op {
 	static __device__ __forceinline__ float add(float a, float b) { if (EXACT) { return __fadd_rn(a, b); } else { return a + b; } }
 	static __device__ __forceinline__ float sub(float a, float b) { if (EXACT) { return __fsub_rn(a, b); } else { return a - b; } }
 	static __device__ __forceinline__ float div(float a, float b) { if (EXACT) { return __fdiv_rn(a, b); } else { return a / b; } }
+	// 1.0f / x: the correctly rounded reciprocal is the correctly rounded quotient, with a shorter instruction sequence
+	static __device__ __forceinline__ float rcp(float x) { if (EXACT) { return __frcp_rn(x); } else { return 1.0f / x; } }
 	static __device__ __forceinline__ double dmul(double a, double b) { if (EXACT) { return __dmul_rn(a, b); } else { return a * b; } }
 	static __device__ __forceinline__ double dadd(double a, double b) { if (EXACT) { return __dadd_rn(a, b); } else { return a + b; } }
 	static __device__ __forceinline__ double dsub(double a, double b) { if (EXACT) { return __dsub_rn(a, b); } else { return a - b; } }
@@ -331,11 +333,11 @@ __device__ __forceinline__ void ConstrainOne(const VS& vs, const PARAMS& p, cons
 template <bool EXACT>
 __device__ __forceinline__ void Cramer2(float A0, float A1, float A2, float b0, float b1, float& l0, float& l1) {
 	typedef Op<EXACT> O;
-	float invA00 = O::div(1.0f, A0);
-	float invA11 = O::div(1.0f, A2);
+	float invA00 = O::rcp(A0);
+	float invA11 = O::rcp(A2);
 	float p0 = O::mul(A1, invA00);
 	float p1 = O::mul(A1, invA11);
-	float invDet = O::div(1.0f, fmaxf(0.00000001f, O::sub(1.0f, O::mul(p0, p1))));
+	float invDet = O::rcp(fmaxf(0.00000001f, O::sub(1.0f, O::mul(p0, p1))));
 	float q0 = O::mul(b0, invA00);
 	float q1 = O::mul(b1, invA11);
 	l0 = O::mul(invDet, O::sub(q0, O::mul(p0, q1)));
@@ -609,7 +611,7 @@ __device__ __forceinline__ void InverseViaDouble(const float (&m)[3][3], float (
 	adj[2][1] = __double2float_rn(-O::dsub(O::dmul(d[0][0], d[2][1]), O::dmul(d[0][1], d[2][0])));
 	adj[2][2] = __double2float_rn(O::dsub(O::dmul(d[0][0], d[1][1]), O::dmul(d[0][1], d[1][0])));
 	float det = O::dot(m[0][0], m[0][1], m[0][2], adj[0][0], adj[1][0], adj[2][0]);
-	float s = O::div(1.0f, det);
+	float s = O::rcp(det);
 #pragma unroll
 	for (int c = 0; c < 3; c++) {
 #pragma unroll
