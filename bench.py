@@ -43,7 +43,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=55, help="block is cells^3 hexes -> 6*cells^3 tets")
     ap.add_argument("--substeps-per-step", type=int, default=50)
     ap.add_argument("--precision", choices=["exact", "fast"], default="exact")
-    ap.add_argument("--schedule", choices=["bricks", "persistent", "per_color"], default="persistent")
+    ap.add_argument("--schedule", choices=["dataflow", "bricks", "persistent", "per_color"], default="dataflow")
     ap.add_argument("--energy", choices=["yeohskinfast", "mixedsel", "mixed", "yeohskin"], default="yeohskinfast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hint", action="store_true", help="use the generic colouring instead of the lattice 24-colouring")
@@ -118,7 +118,7 @@ def make_scene(xf, args, device, stream):
     nodes, idx, hint = xf.GenerateTetBlock(args.cells, args.cells)
     geo = xf.GeoLinear3dCuda(nodes, idx, device=device, stream=stream,
                              precision=xf.PRECISION_EXACT if args.precision == "exact" else xf.PRECISION_FAST,
-                             schedule={"bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
+                             schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
                              color_hint=None if args.no_hint else hint)
     y_min = float(nodes.reshape(-1, 3)[:, 1].min())
     geo.set_ground(True, y_min - 1.0e-3, 0.0)
@@ -333,7 +333,7 @@ def main():
             "bound": "hbm", "achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "traffic": traffic,
             "traffic_source": "profiles/r1_traffic.json (ncu --set full, same kernel and workload)" if traffic else None,
             "algorithmic_bytes_per_launch": nT * sub * b_hbm,
-            "peak_source": peak_src, "kernel": {"bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent", "per_color": "k_sweep_color (x colours)"}[args.schedule],
+            "peak_source": peak_src, "kernel": {"dataflow": "k_substeps_dataflow", "bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent", "per_color": "k_sweep_color (x colours)"}[args.schedule],
             "bytes_per_element_substep": b_hbm, "units_per_launch": per_launch_units, "kernel_ms": kernel_ms,
             "achieved_l2_gbs": ach_l2, "bytes_per_element_substep_l2": b_l2, "working_set_bytes": ws, "l2_bytes": info["l2Bytes"],
             "headline_rule": "L2 figure iff working set <= l2/2 (SURVEY 8d); here %s" % ("L2" if ws <= info["l2Bytes"] / 2 else "HBM"),

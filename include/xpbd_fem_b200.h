@@ -117,7 +117,11 @@ typedef enum xf_schedule {
 	XF_SCHEDULE_AUTO = 0,
 	XF_SCHEDULE_LAUNCH_PER_COLOR = 1, /* one kernel launch per colour phase */
 	XF_SCHEDULE_PERSISTENT = 2,       /* one cooperative launch per xf_substep call, grid barriers between colours */
-	XF_SCHEDULE_BRICKS = 3            /* PERSISTENT + vertices private to a CTA's brick of elements kept in shared memory */
+	XF_SCHEDULE_BRICKS = 3,           /* PERSISTENT + vertices private to a CTA's brick of elements kept in shared memory */
+	XF_SCHEDULE_DATAFLOW = 4          /* one co-resident launch, NO barriers: vertex records carry the stage that wrote them and
+	                                     every element re-gathers until its four records carry the expected stage.  Same serial
+	                                     order and bits as the others.  Calls that need volume passes, damping sweeps or
+	                                     in-constraint Rayleigh damping run as XF_SCHEDULE_PERSISTENT. */
 } xf_schedule;
 
 typedef struct xf_create_params {

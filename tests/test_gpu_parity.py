@@ -5,6 +5,7 @@ running the schedule's equivalent serial order.
 XF_PRECISION_EXACT: bit-exact (positions, velocities, inverse masses, volume) - the bar is equality.
 XF_PRECISION_FAST : FMA contraction; the bar is north_star's 1e-5 x bounding box per substep."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -16,7 +17,9 @@ build()
 xf = load_package()
 pytestmark = pytest.mark.gpu
 DT = np.float32(1.0 / 3000.0)
-SCHEDULES = [xf.SCHEDULE_BRICKS, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
+SCHEDULES = [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_BRICKS, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
+if os.environ.get("XF_TEST_SCHEDULES"):  # development aid: restrict the schedule axis, e.g. XF_TEST_SCHEDULES=4
+    SCHEDULES = [int(x) for x in os.environ["XF_TEST_SCHEDULES"].split(",")]
 
 
 def settings_pair(**kw):

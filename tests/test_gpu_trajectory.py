@@ -101,6 +101,9 @@ def test_full_size_properties(big):
     b = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_LAUNCH_PER_COLOR, color_hint=hint)
     p = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_PERSISTENT, color_hint=hint)
     p.Substep(st, DT, 60)
+    d = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_DATAFLOW, color_hint=hint)
+    for n in (1, 2, 57):  # several launches: the stage tags continue across calls
+        d.Substep(st, DT, n)
     assert a.nT == 998250 and a.nV == 175616 and a.nColors == 24
     vol0 = a.CalculateVolume()
     a.Substep(st, DT, 60)
@@ -109,6 +112,8 @@ def test_full_size_properties(big):
     Xb, Vb, wb = b.get_state()
     assert np.array_equal(Xa, Xb) and np.array_equal(Va, Vb) and np.array_equal(wa, wb)  # schedule independence
     assert np.array_equal(Xa, p.get_state()[0])
+    Xd, Vd, wd = d.get_state()
+    assert np.array_equal(Xa, Xd) and np.array_equal(Va, Vd) and np.array_equal(wa, wd)  # barrier-free schedule: same bits
     assert np.isfinite(Xa).all() and np.isfinite(Va).all()
     assert abs(a.CalculateVolume() / vol0 - 1.0) < 2e-4                                  # volume preservation
     flags = a.get_rest()[2]

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem
 XF_ABI_VERSION = 1
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
 PRECISION_EXACT, PRECISION_FAST = 0, 1
-SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT, SCHEDULE_BRICKS = 0, 1, 2, 3
+SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT, SCHEDULE_BRICKS, SCHEDULE_DATAFLOW = 0, 1, 2, 3, 4
 
 # flag word (Settings.h:9-75)
 Settings_EnergyBit = 6

@@ -1,6 +1,7 @@
 // C ABI of libxpbd_fem_b200.so (include/xpbd_fem_b200.h): scene lifetime, uploads, stepping, state access.
 // Host C++ only; every device operation goes through the launchers in xf_kernels.cu.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -52,6 +53,9 @@ struct xf_scene {
 	int schedule = XF_SCHEDULE_AUTO;
 	bool cooperative = false;
 	std::map<uint32_t, LaunchShape> shapes; // per energy
+	bool dataflowOk = false;  // stage codes fit the vertex-index top byte / the 24-bit record tag
+	uint32_t verBase = 1;     // first stage tag of the next dataflow launch (24-bit, wraps)
+	uint32_t spinSleepNs = 0; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
 	int smCount = 0;
 	size_t l2Bytes = 0;
 	uint64_t launches = 0;
@@ -74,7 +78,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -110,6 +114,22 @@ int UploadScene(xf_scene* s) {
 	XF_CUDA(Upload(&d.eC, pk.c));
 	XF_CUDA(Upload(&d.eArea, pk.area));
 	XF_CUDA(Upload(&d.eAb, pkb.a));
+	// dataflow schedule: previous-writer stage code per (element, vertex) in the top byte of the index, last-writer code per vertex
+	s->dataflowOk = m.nV <= 0x01000000u && d.nColors <= 254u;
+	if (s->dataflowOk) {
+		std::vector<uint8_t> lastCode(m.nV, 0);
+		std::vector<ElemRecA> ad = pk.a;
+		for (uint32_t k = 0; k < m.nT; k++) { // device order is colour-major: a vertex's elements are met in colour order
+			const uint32_t code = 1u + m.color[bp.deviceOrder[k]];
+			for (int j = 0; j < 4; j++) {
+				const uint32_t v = pk.a[k].idx[j];
+				ad[k].idx[j] = v | ((uint32_t)lastCode[v] << 24);
+				lastCode[v] = (uint8_t)code;
+			}
+		}
+		XF_CUDA(Upload(&d.eAd, ad));
+		XF_CUDA(Upload(&d.lastCode, lastCode));
+	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
 	XF_CUDA(Upload(&d.brickStart, bp.brickStart));
 	XF_CUDA(Upload(&d.privStart, bp.privStart));
@@ -182,7 +202,7 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 	*outScene = nullptr;
 	if (params->abiVersion != XF_ABI_VERSION) { return Fail(XF_ERR_INVALID, "xf_create_params.abiVersion mismatch"); }
 	if (params->precision != XF_PRECISION_EXACT && params->precision != XF_PRECISION_FAST) { return Fail(XF_ERR_INVALID, "bad precision"); }
-	if (params->schedule < XF_SCHEDULE_AUTO || params->schedule > XF_SCHEDULE_BRICKS) { return Fail(XF_ERR_INVALID, "bad schedule"); }
+	if (params->schedule < XF_SCHEDULE_AUTO || params->schedule > XF_SCHEDULE_DATAFLOW) { return Fail(XF_ERR_INVALID, "bad schedule"); }
 	xf_scene* s = new (std::nothrow) xf_scene();
 	if (!s) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
 	std::string err;
@@ -210,10 +230,17 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		}
 		rc = UploadScene(s);
 		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
-		if (s->schedule == XF_SCHEDULE_AUTO) { s->schedule = s->cooperative ? XF_SCHEDULE_PERSISTENT : XF_SCHEDULE_LAUNCH_PER_COLOR; } // BRICKS measured slower, see xf_bricks.cu
+		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env); }
+		if (s->schedule == XF_SCHEDULE_AUTO) { // BRICKS measured slower, see xf_bricks.cu
+			s->schedule = !s->cooperative ? XF_SCHEDULE_LAUNCH_PER_COLOR : (s->dataflowOk ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_PERSISTENT);
+		}
+		if (s->schedule == XF_SCHEDULE_DATAFLOW && !s->dataflowOk) {
+			FreeDevice(s); delete s;
+			return Fail(XF_ERR_UNSUPPORTED, "XF_SCHEDULE_DATAFLOW needs <= 2^24 vertices and <= 254 colours");
+		}
 		if (s->schedule >= XF_SCHEDULE_PERSISTENT && !s->cooperative) {
 			FreeDevice(s); delete s;
-			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT / XF_SCHEDULE_BRICKS)");
+			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT / BRICKS / DATAFLOW)");
 		}
 	}
 	*outScene = s;
@@ -263,9 +290,21 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 	rc = BuildParams(s, st, manip, dt, &p);
 	if (rc != XF_OK) { return rc; }
 	const bool exact = s->precision == XF_PRECISION_EXACT;
-	if (s->schedule == XF_SCHEDULE_BRICKS) {
+	// the barrier-free schedule covers the undamped main sweep; everything else runs with grid barriers
+	const bool plainSweep = !(p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST) && !p.doDamp && !p.doPbdDamp && p.volumePasses == 0;
+	if (s->schedule == XF_SCHEDULE_DATAFLOW && plainSweep) {
+		const uint32_t stride = p.nColors + 1u;
+		const uint32_t maxPerLaunch = (0x00ffffffu - 2u) / stride; // tags of one launch must not wrap onto the stale ones
+		for (uint32_t done = 0; done < n;) {
+			const uint32_t m = std::min(n - done, maxPerLaunch);
+			p.tickId = st->tickId + done;
+			XF_CUDA(LaunchSubstepsDataflow(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
+			s->verBase = (s->verBase + m * stride + 1u) & 0x00ffffffu;
+			done += m;
+		}
+	} else if (s->schedule == XF_SCHEDULE_BRICKS) {
 		XF_CUDA(LaunchSubstepsBricks(s->dev, p, exact, n, s->smCount, s->stream, &s->launches));
-	} else if (s->schedule == XF_SCHEDULE_PERSISTENT) {
+	} else if (s->schedule == XF_SCHEDULE_PERSISTENT || s->schedule == XF_SCHEDULE_DATAFLOW) {
 		auto it = s->shapes.find(p.energy);
 		if (it == s->shapes.end()) {
 			LaunchShape shape;
@@ -442,6 +481,9 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 	out->smCount = (uint32_t)s->smCount;
 	if (s->schedule == XF_SCHEDULE_BRICKS) {
 		out->gridBlocks = s->dev.nBricks;
+		out->blockThreads = 256;
+	} else if (s->schedule == XF_SCHEDULE_DATAFLOW) {
+		out->gridBlocks = (uint32_t)(2 * s->smCount);
 		out->blockThreads = 256;
 	} else if (!s->shapes.empty()) {
 		out->gridBlocks = (uint32_t)s->shapes.begin()->second.gridBlocks;

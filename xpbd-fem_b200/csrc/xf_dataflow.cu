@@ -1,0 +1,163 @@
+// XF_SCHEDULE_DATAFLOW — the persistent sweep without any barrier.
+//
+// The colour schedule (xf_prepare.cpp) is kept — same elements, same equivalent serial order, same bits — but the
+// grid-wide barrier between colours is replaced by *versioned vertex records*.  A vertex record is one 32-byte L2
+// sector {x, y, z, w, flags} that always moves with ONE 256-bit strong access (LDG/STG.E.ENL2.256.STRONG.GPU), so a
+// reader sees either the old or the new record, never a mix.  The upper 24 bits of `flags` carry the *stage* that
+// wrote the record:
+//     stage(substep s, vertex phase) = base + s*(nC+1)
+//     stage(substep s, colour c)     = base + s*(nC+1) + 1 + c
+// Every writer of a vertex knows which stage wrote it last: for an element that is the colour of the previous element
+// around the vertex (or the vertex phase), precomputed on the host and carried in the top byte of each vertex index;
+// for the vertex phase it is the last colour around the vertex (`lastCode`).  A thread gathers its four records and
+// simply re-gathers until all four carry the expected stage, then solves and scatters the records stamped with its own
+// stage.  Elements touching one vertex are totally ordered by colour, so between "predecessor wrote" and "I write"
+// nobody else touches the record: no fences, no flags, no atomics, no barrier of any scope.
+//
+// Deadlock freedom: the kernel is launched cooperatively (all CTAs co-resident); every thread walks its work in stage
+// order and every item depends only on items of strictly earlier stages, so the unfinished item of minimal stage is
+// always runnable by a thread that is not waiting for anything else.
+//
+// Why: at 1M tets a colour holds only ~41.6k elements (9 warps per SM); the per-colour cost of the barrier schedule was
+// 1.2 us of grid barrier + arrival skew + ~1 us element latency, 25 times per substep.  Here the only serialisation left
+// is the true data dependence: predecessor's store -> L2 -> my load.
+//
+// Covers the main sweep (all energies / solve modes, undamped in-constraint) + the fused vertex phase.  Volume passes,
+// damping sweeps and in-constraint Rayleigh damping (which reads O of other threads' vertices) run on
+// XF_SCHEDULE_PERSISTENT; xf_substep falls back per call.
+#include "xf_dispatch.cuh"
+#include "xf_element.cuh"
+#include "xf_phase.cuh"
+
+namespace xf {
+
+namespace {
+
+constexpr uint32_t kVerMask = 0xffffff00u;
+// A record that never reaches the expected stage means a broken schedule (or a caller that rewrote the state while a
+// launch was in flight): fail loudly (launch error) instead of hanging the device.  2^24 polls is seconds, a healthy
+// wait is a few polls.
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+template <bool EXACT>
+__device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict, bool wait,
+                                               uint32_t expectTag, uint32_t newTag, uint32_t sleepNs) {
+	VertexRegs v = LoadVertex(sc.Xw, i);
+	if (wait) {
+		uint32_t spins = 0;
+		while ((v.flags & kVerMask) != expectTag) {
+			if (++spins > kSpinLimit) { __trap(); }
+			if (sleepNs) { __nanosleep(sleepNs); }
+			v = LoadVertex(sc.Xw, i);
+		}
+	}
+	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict);
+	v.flags = (v.flags & 0xffu) | newTag;
+	StoreVertex(sc.Xw, i, v);
+}
+
+// One element: spin-gather the four versioned records, solve, scatter with this stage's tag.
+template <int ENERGY, bool SIMUL, bool EXACT>
+__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t stageBase, uint32_t c) {
+	const GlobalStore vs = StoreOf(sc);
+	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
+	uint32_t vid[4], expectTag[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		vid[n] = raw[n] & 0x00ffffffu;
+		expectTag[n] = (stageBase + (raw[n] >> 24)) << 8;
+	}
+	VertexRegs v[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(vid[n]); }
+	for (uint32_t spins = 0;; spins++) {
+		if (spins > kSpinLimit) { __trap(); }
+		bool ok[4];
+#pragma unroll
+		for (int n = 0; n < 4; n++) { ok[n] = (v[n].flags & kVerMask) == expectTag[n]; }
+		if (ok[0] && ok[1] && ok[2] && ok[3]) { break; }
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			if (!ok[n]) { v[n] = vs.LoadX(vid[n]); }
+		}
+	}
+	const uint32_t newTag = (stageBase + 1u + c) << 8;
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
+	ElemRec r = rec;
+	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v);
+}
+
+template <int ENERGY, bool EXACT>
+__device__ __forceinline__ void DataflowLoad(const DeviceScene& sc, uint32_t e, ElemRec& rec) {
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
+}
+
+}  // namespace
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
+                                                              uint32_t verBase, uint32_t sleepNs) {
+	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t gsize = gridDim.x * blockDim.x;
+	const uint32_t slot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
+	const uint32_t nC = p.nColors;
+	const uint32_t stride = nC + 1u;
+	ElemRec rec;
+	for (uint32_t s = 0; s < nSubsteps; s++) {
+		const uint32_t stageBase = verBase + s * stride;
+		if (p.colorStart[0] + slot < p.colorStart[1]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[0] + slot, rec); }
+		// vertex phase: post of the previous substep + predict, once the vertex's last element of that substep has written
+		for (uint32_t i = gtid; i < sc.nV; i += gsize) {
+			const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+			DataflowVertex<EXACT>(sc, p, i, s > 0, true, s > 0, expectTag, stageBase << 8, sleepNs);
+		}
+		for (uint32_t c = 0; c < nC; c++) {
+			const uint32_t end = p.colorStart[c + 1];
+			uint32_t e = p.colorStart[c] + slot;
+			if (e < end) { DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, rec, stageBase, c); }
+			for (e += gsize; e < end; e += gsize) {
+				ElemRec more;
+				DataflowLoad<ENERGY, EXACT>(sc, e, more);
+				DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, more, stageBase, c);
+			}
+			if (c + 1 < nC && p.colorStart[c + 1] + slot < p.colorStart[c + 2]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + slot, rec); }
+		}
+	}
+	// closing post phase (locks, manipulator, velocities) of the last substep
+	const uint32_t lastBase = verBase + (nSubsteps - 1u) * stride;
+	for (uint32_t i = gtid; i < sc.nV; i += gsize) {
+		const uint32_t expectTag = (lastBase + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+		DataflowVertex<EXACT>(sc, p, i, true, false, true, expectTag, (lastBase + stride) << 8, sleepNs);
+	}
+}
+
+namespace {
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct DataflowRunner {
+	static cudaError_t Run(const DeviceScene& sc, const SubstepParams& p, uint32_t nSubsteps, int smCount, uint32_t verBase, uint32_t sleepNs,
+	                       cudaStream_t st, uint64_t* launches) {
+		auto fn = k_substeps_dataflow<ENERGY, SIMUL, EXACT>;
+		static int perSm = 0; // per instantiation; the occupancy of a kernel does not change
+		if (perSm == 0) {
+			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, 0);
+			if (e != cudaSuccess) { return e; }
+			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		}
+		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&sleepNs };
+		// cooperative launch: not for grid.sync (there is none) but because it guarantees that all CTAs are co-resident
+		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, 0, st);
+		++*launches;
+		return e;
+	}
+};
+}  // namespace
+
+cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                   uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount) {
+	return DispatchConfig<DataflowRunner>(p.energy, p.simultaneous != 0, exact, false, sc, p, nSubsteps, smCount, verBase, sleepNs, stream, launchCount);
+}
+
+}  // namespace xf

@@ -67,6 +67,10 @@ struct DeviceScene {
 	uint32_t nSharedVerts = 0;
 	uint32_t maxPrivPerBrick = 0;
 	unsigned int* barrier = nullptr; // grid-barrier counter
+	// dataflow schedule (XF_SCHEDULE_DATAFLOW, xf_dataflow.cu): eA whose vertex indices carry, in their top byte, the stage
+	// code of the previous writer of that vertex (0 = vertex phase, 1 + colour otherwise); per vertex the code of its last writer
+	ElemRecA* eAd = nullptr;
+	uint8_t* lastCode = nullptr;
 };
 
 constexpr int kMaxHandles = 64;
@@ -187,6 +191,8 @@ cudaError_t LaunchSubstepsPerColor(const DeviceScene& sc, const SubstepParams& p
                                    uint64_t* launchCount);
 cudaError_t LaunchSubstepsBricks(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, cudaStream_t stream,
                                  uint64_t* launchCount);
+cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                   uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
                                      cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchElementVolumes(const DeviceScene& sc, cudaStream_t stream, uint64_t* launchCount);  // -> sc.eScratch, stream order
