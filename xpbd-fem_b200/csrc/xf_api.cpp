@@ -56,6 +56,7 @@ struct xf_scene {
 	bool dataflowOk = false;  // stage codes fit the vertex-index top byte / the 24-bit record tag
 	uint32_t verBase = 1;     // first stage tag of the next dataflow launch (24-bit, wraps)
 	uint32_t spinSleepNs = 0; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
+	std::vector<uint32_t> intOfExt, extOfInt; // caller's vertex id <-> device vertex id
 	int smCount = 0;
 	size_t l2Bytes = 0;
 	uint64_t launches = 0;
@@ -78,7 +79,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -90,30 +91,63 @@ int UploadScene(xf_scene* s) {
 	d.nV = m.nV;
 	d.nT = m.nT;
 	d.nColors = (uint32_t)m.colorStart.size() - 1;
+	// element planes: colour-major; inside a colour in stream order, or (XF_SCHEDULE_BRICKS) grouped by brick, one brick
+	// per CTA of the persistent grid (2 CTAs x 256 threads per SM)
+	const bool bricks = s->schedule == XF_SCHEDULE_BRICKS;
+	BrickPlan bp;
+	BuildBricks(m, bricks ? (uint32_t)(2 * s->smCount) : 1u, kBrickSlotCap, &bp);
+	// Device vertex numbering.  A warp handles 32 consecutive elements of one colour and its lanes gather/scatter corner n
+	// of their element with one 256-bit access each; every distinct 128-byte line costs one L1TEX wavefront, and the sweep's
+	// per-element cost IS those wavefronts (~276 per warp-element when every lane hits its own line).  Numbering the vertices
+	// in first-touch order (colour-major, corner-major, element-minor) makes consecutive lanes touch consecutive records
+	// wherever the mesh allows it (exactly so on MeshGen lattices: four interleaved row-ordered classes), i.e. four lanes
+	// per line.  The caller's numbering is restored at the ABI (pack/unpack kernels, handle and manipulator indices).
+	s->intOfExt.assign(m.nV, 0xffffffffu);
+	s->extOfInt.clear();
+	s->extOfInt.reserve(m.nV);
+	if (!bricks && !getenv("XF_NO_RENUMBER")) {
+		for (uint32_t c = 0; c < d.nColors; c++) {
+			for (int j = 0; j < 4; j++) {
+				for (uint32_t k = m.colorStart[c]; k < m.colorStart[c + 1]; k++) {
+					const uint32_t v = m.idx[4 * (size_t)bp.deviceOrder[k] + j];
+					if (s->intOfExt[v] == 0xffffffffu) { s->intOfExt[v] = (uint32_t)s->extOfInt.size(); s->extOfInt.push_back(v); }
+				}
+			}
+		}
+	}
+	for (uint32_t v = 0; v < m.nV; v++) { // vertices no element touches (or all of them: identity numbering)
+		if (s->intOfExt[v] == 0xffffffffu) { s->intOfExt[v] = (uint32_t)s->extOfInt.size(); s->extOfInt.push_back(v); }
+	}
 	std::vector<VertexRec> xw(m.nV);
 	std::vector<double4> x0(m.nV), zero(m.nV, double4{ 0.0, 0.0, 0.0, 0.0 });
 	for (uint32_t i = 0; i < m.nV; i++) {
-		xw[i] = VertexRec{ m.X0[3 * (size_t)i], m.X0[3 * (size_t)i + 1], m.X0[3 * (size_t)i + 2], m.w[i], (uint32_t)m.flags[i] };
+		const uint32_t v = s->extOfInt[i];
+		xw[i] = VertexRec{ m.X0[3 * (size_t)v], m.X0[3 * (size_t)v + 1], m.X0[3 * (size_t)v + 2], m.w[v], (uint32_t)m.flags[v] };
 		x0[i] = double4{ xw[i].x, xw[i].y, xw[i].z, 0.0 };
 	}
 	XF_CUDA(Upload(&d.Xw, xw));
 	XF_CUDA(Upload(&d.O, x0));
 	XF_CUDA(Upload(&d.X0, x0));
 	XF_CUDA(Upload(&d.V, zero));
-	// element planes: colour-major, brick-minor (one brick per CTA of the persistent grid: 2 CTAs x 256 threads per SM)
-	BrickPlan bp;
-	BuildBricks(m, (uint32_t)(2 * s->smCount), kBrickSlotCap, &bp);
+	XF_CUDA(Upload(&d.extOfInt, s->extOfInt));
 	std::vector<uint32_t> streamToSorted(m.nT), canonPos(m.nT), serialPos(m.nT);
 	for (uint32_t pos = 0; pos < m.nT; pos++) { serialPos[m.order[pos]] = pos; }
 	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[bp.deviceOrder[pos]] = pos; canonPos[pos] = serialPos[bp.deviceOrder[pos]]; }
-	PackedElements pk, pkb;
-	PackElements(m, bp.deviceOrder, nullptr, &pk);
-	PackElements(m, bp.deviceOrder, bp.encodedIdx.data(), &pkb);
+	std::vector<uint32_t> devIdx(4 * (size_t)m.nT);
+	for (uint32_t k = 0; k < m.nT; k++) {
+		for (int j = 0; j < 4; j++) { devIdx[4 * (size_t)k + j] = s->intOfExt[m.idx[4 * (size_t)bp.deviceOrder[k] + j]]; }
+	}
+	PackedElements pk;
+	PackElements(m, bp.deviceOrder, devIdx.data(), &pk);
 	XF_CUDA(Upload(&d.eA, pk.a));
 	XF_CUDA(Upload(&d.eB, pk.b));
 	XF_CUDA(Upload(&d.eC, pk.c));
 	XF_CUDA(Upload(&d.eArea, pk.area));
-	XF_CUDA(Upload(&d.eAb, pkb.a));
+	if (bricks) { // identity vertex numbering here: the brick plan speaks the caller's ids
+		PackedElements pkb;
+		PackElements(m, bp.deviceOrder, bp.encodedIdx.data(), &pkb);
+		XF_CUDA(Upload(&d.eAb, pkb.a));
+	}
 	// dataflow schedule: previous-writer stage code per (element, vertex) in the top byte of the index, last-writer code per vertex
 	s->dataflowOk = m.nV <= 0x01000000u && d.nColors <= 254u;
 	if (s->dataflowOk) {
@@ -131,13 +165,15 @@ int UploadScene(xf_scene* s) {
 		XF_CUDA(Upload(&d.lastCode, lastCode));
 	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
-	XF_CUDA(Upload(&d.brickStart, bp.brickStart));
-	XF_CUDA(Upload(&d.privStart, bp.privStart));
-	XF_CUDA(Upload(&d.privVerts, bp.privVerts));
-	XF_CUDA(Upload(&d.sharedVerts, bp.sharedVerts));
-	d.nBricks = bp.nBricks;
-	d.nSharedVerts = (uint32_t)bp.sharedVerts.size();
-	d.maxPrivPerBrick = bp.maxPrivPerBrick;
+	if (bricks) {
+		XF_CUDA(Upload(&d.brickStart, bp.brickStart));
+		XF_CUDA(Upload(&d.privStart, bp.privStart));
+		XF_CUDA(Upload(&d.privVerts, bp.privVerts));
+		XF_CUDA(Upload(&d.sharedVerts, bp.sharedVerts));
+		d.nBricks = bp.nBricks;
+		d.nSharedVerts = (uint32_t)bp.sharedVerts.size();
+		d.maxPrivPerBrick = bp.maxPrivPerBrick;
+	}
 	XF_CUDA(Upload(&d.streamToSorted, streamToSorted));
 	XF_CUDA(cudaMalloc((void**)&d.eScratch, sizeof(float) * m.nT));
 	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
@@ -166,6 +202,10 @@ int BuildParams(xf_scene* s, const xf_settings* st, const xf_manipulator* manip,
 	p->groundKeep = 1.0f - s->groundFriction;
 	p->handleCount = s->handleCount;
 	memcpy(p->handleIdx, s->handleIdx, sizeof(p->handleIdx));
+	if (!s->intOfExt.empty()) { // device vertex numbering
+		if (p->manipOn) { p->manipIdx = s->intOfExt[p->manipIdx]; }
+		for (uint32_t h = 0; h < p->handleCount; h++) { p->handleIdx[h] = s->intOfExt[p->handleIdx[h]]; }
+	}
 	memcpy(p->handleTarget, s->handleTarget, sizeof(p->handleTarget));
 	return XF_OK;
 }
@@ -230,7 +270,8 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		}
 		rc = UploadScene(s);
 		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
-		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env); }
+		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env) & 0xffffu; }
+		if (const char* env = getenv("XF_DATAFLOW_ESLEEP_NS")) { s->spinSleepNs |= ((uint32_t)atoi(env) & 0xffffu) << 16; }
 		if (s->schedule == XF_SCHEDULE_AUTO) { // BRICKS measured slower, see xf_bricks.cu
 			s->schedule = !s->cooperative ? XF_SCHEDULE_LAUNCH_PER_COLOR : (s->dataflowOk ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_PERSISTENT);
 		}
@@ -412,7 +453,10 @@ int xf_get_rest(xf_scene* s, double* X0, double* O, uint8_t* flags) {
 		std::vector<double4> tmp(m.nV);
 		XF_CUDA(cudaStreamSynchronize(s->stream));
 		XF_CUDA(cudaMemcpy(tmp.data(), s->dev.O, sizeof(double4) * m.nV, cudaMemcpyDeviceToHost));
-		for (uint32_t i = 0; i < m.nV; i++) { O[3 * (size_t)i] = tmp[i].x; O[3 * (size_t)i + 1] = tmp[i].y; O[3 * (size_t)i + 2] = tmp[i].z; }
+		for (uint32_t i = 0; i < m.nV; i++) {
+			const uint32_t v = s->extOfInt[i];
+			O[3 * (size_t)v] = tmp[i].x; O[3 * (size_t)v + 1] = tmp[i].y; O[3 * (size_t)v + 2] = tmp[i].z;
+		}
 	}
 	return XF_OK;
 }

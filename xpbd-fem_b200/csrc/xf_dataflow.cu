@@ -57,8 +57,9 @@ __device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const Subs
 }
 
 // One element: spin-gather the four versioned records, solve, scatter with this stage's tag.
-template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t stageBase, uint32_t c) {
+template <int ENERGY, bool SIMUL, bool EXACT, bool SENTINEL>
+__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t stageBase, uint32_t c,
+                                                uint32_t sleepNs) {
 	const GlobalStore vs = StoreOf(sc);
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4];
@@ -66,6 +67,26 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 	for (int n = 0; n < 4; n++) {
 		vid[n] = raw[n] & 0x00ffffffu;
 		expectTag[n] = (stageBase + (raw[n] >> 24)) << 8;
+	}
+	// Polling is not free: a gather of 32 scattered records is up to 32 L1TEX wavefronts, the very resource the sweep is
+	// bound by.  So one lane polls ONE sentinel record (the corner whose previous writer is the latest stage) until it
+	// carries the expected tag (one wavefront per poll), and only then does the warp gather; stale records of the real
+	// gather are re-read lane by lane.
+	if (SENTINEL) {
+		const unsigned mask = __activemask();
+		if ((threadIdx.x & 31u) == (uint32_t)(__ffs(mask) - 1)) {
+			uint32_t bestRaw = raw[0];
+#pragma unroll
+			for (int n = 1; n < 4; n++) { bestRaw = (raw[n] >> 24) > (bestRaw >> 24) ? raw[n] : bestRaw; }
+			const uint32_t bestVid = bestRaw & 0x00ffffffu, bestTag = (stageBase + (bestRaw >> 24)) << 8;
+			for (uint32_t spins = 0;; spins++) {
+				if (spins > kSpinLimit) { __trap(); }
+				const VertexRegs sv = vs.LoadX(bestVid);
+				if ((sv.flags & kVerMask) == bestTag) { break; }
+				if (sleepNs) { __nanosleep(sleepNs); }
+			}
+		}
+		__syncwarp(mask);
 	}
 	VertexRegs v[4];
 #pragma unroll
@@ -76,6 +97,7 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 #pragma unroll
 		for (int n = 0; n < 4; n++) { ok[n] = (v[n].flags & kVerMask) == expectTag[n]; }
 		if (ok[0] && ok[1] && ok[2] && ok[3]) { break; }
+		if (sleepNs) { __nanosleep(sleepNs); }
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
 			if (!ok[n]) { v[n] = vs.LoadX(vid[n]); }
@@ -105,6 +127,8 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 	const uint32_t slot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
 	const uint32_t nC = p.nColors;
 	const uint32_t stride = nC + 1u;
+	const uint32_t elemSleepNs = sleepNs >> 16; // packed: low 16 bits vertex-phase back-off, high 16 bits element back-off
+	sleepNs &= 0xffffu;
 	ElemRec rec;
 	for (uint32_t s = 0; s < nSubsteps; s++) {
 		const uint32_t stageBase = verBase + s * stride;
@@ -117,11 +141,11 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 		for (uint32_t c = 0; c < nC; c++) {
 			const uint32_t end = p.colorStart[c + 1];
 			uint32_t e = p.colorStart[c] + slot;
-			if (e < end) { DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, rec, stageBase, c); }
+			if (e < end) { DataflowElement<ENERGY, SIMUL, EXACT, true>(sc, p, rec, stageBase, c, elemSleepNs); }
 			for (e += gsize; e < end; e += gsize) {
 				ElemRec more;
 				DataflowLoad<ENERGY, EXACT>(sc, e, more);
-				DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, more, stageBase, c);
+				DataflowElement<ENERGY, SIMUL, EXACT, false>(sc, p, more, stageBase, c, elemSleepNs);
 			}
 			if (c + 1 < nC && p.colorStart[c + 1] + slot < p.colorStart[c + 2]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + slot, rec); }
 		}

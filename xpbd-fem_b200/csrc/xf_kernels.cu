@@ -209,19 +209,21 @@ __global__ void __launch_bounds__(256) k_pack_state(const DeviceScene sc, double
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= sc.nV) { return; }
 	VertexRegs v = LoadVertex(sc.Xw, i);
-	if (X) { X[3 * (size_t)i] = v.x[0]; X[3 * (size_t)i + 1] = v.x[1]; X[3 * (size_t)i + 2] = v.x[2]; }
-	if (V) { double vel[3]; LoadD3(sc.V, i, vel); V[3 * (size_t)i] = vel[0]; V[3 * (size_t)i + 1] = vel[1]; V[3 * (size_t)i + 2] = vel[2]; }
-	if (W) { W[i] = v.w; }
+	const size_t x = sc.extOfInt ? __ldg(sc.extOfInt + i) : i; // the caller's numbering
+	if (X) { X[3 * x] = v.x[0]; X[3 * x + 1] = v.x[1]; X[3 * x + 2] = v.x[2]; }
+	if (V) { double vel[3]; LoadD3(sc.V, i, vel); V[3 * x] = vel[0]; V[3 * x + 1] = vel[1]; V[3 * x + 2] = vel[2]; }
+	if (W) { W[x] = v.w; }
 }
 __global__ void __launch_bounds__(256) k_unpack_state(const DeviceScene sc, const double* __restrict__ X, const double* __restrict__ V,
                                                       const float* __restrict__ W) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= sc.nV) { return; }
 	VertexRegs v = LoadVertex(sc.Xw, i);
-	if (X) { v.x[0] = X[3 * (size_t)i]; v.x[1] = X[3 * (size_t)i + 1]; v.x[2] = X[3 * (size_t)i + 2]; }
-	if (W) { v.w = W[i]; }
+	const size_t x = sc.extOfInt ? __ldg(sc.extOfInt + i) : i; // the caller's numbering
+	if (X) { v.x[0] = X[3 * x]; v.x[1] = X[3 * x + 1]; v.x[2] = X[3 * x + 2]; }
+	if (W) { v.w = W[x]; }
 	StoreVertex(sc.Xw, i, v);
-	if (V) { double vel[3] = { V[3 * (size_t)i], V[3 * (size_t)i + 1], V[3 * (size_t)i + 2] }; StoreD3(sc.V, i, vel); }
+	if (V) { double vel[3] = { V[3 * x], V[3 * x + 1], V[3 * x + 2] }; StoreD3(sc.V, i, vel); }
 }
 
 // fp64 statistics: volume, kinetic, gravitational, deviatoric, volumetric, non-finite count.

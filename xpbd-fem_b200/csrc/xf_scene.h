@@ -71,6 +71,8 @@ struct DeviceScene {
 	// code of the previous writer of that vertex (0 = vertex phase, 1 + colour otherwise); per vertex the code of its last writer
 	ElemRecA* eAd = nullptr;
 	uint8_t* lastCode = nullptr;
+	// device vertex id -> caller's vertex id (nullptr = identity); used where state crosses the ABI
+	uint32_t* extOfInt = nullptr;
 };
 
 constexpr int kMaxHandles = 64;
