@@ -1,20 +1,17 @@
 #!/bin/bash
-# Round-1 measurement sweep of the barrier-free schedule and the device vertex numbering (run under gpurun).
+# Round-1 measurement sweep of the barrier-free schedule (run under gpurun).
 mkdir -p gpurun_out
-B="timeout 300 python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
+B="timeout 120 python bench.py --steps 5 --warmup 3 --no-cpu-baseline"
 {
-XF_TEST_SCHEDULES=4,2 timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -5
-timeout 600 python -m pytest tests/test_gpu_trajectory.py -x -q -m gpu -k "full_size" 2>&1 | tail -5
-echo "== persistent, no renumber"; XF_NO_RENUMBER=1 $B --schedule persistent
-echo "== persistent, renumber"; $B --schedule persistent
-echo "== dataflow, no renumber"; XF_NO_RENUMBER=1 $B --schedule dataflow
-echo "== dataflow, renumber"; $B --schedule dataflow
-for es in 100 300; do
-  echo "== dataflow, renumber, esleep $es"; XF_DATAFLOW_ESLEEP_NS=$es XF_DATAFLOW_SLEEP_NS=$es $B --schedule dataflow
-done
-for cells in 16 28 40 70 110; do
-  echo "== dataflow cells $cells"; $B --schedule dataflow --cells $cells --substeps-per-step 20
-  echo "== persistent cells $cells"; $B --schedule persistent --cells $cells --substeps-per-step 20
+for mode in 0; do
+  echo "== mode $mode tests"
+  XF_DATAFLOW_MODE=$mode XF_TEST_SCHEDULES=4 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -m gpu  2>&1 | tail -15
+  echo "== mode $mode dataflow"; XF_DATAFLOW_MODE=$mode $B --schedule dataflow
+  echo "== mode $mode dataflow esleep 200"; XF_DATAFLOW_MODE=$mode XF_DATAFLOW_ESLEEP_NS=200 XF_DATAFLOW_SLEEP_NS=200 $B --schedule dataflow
+  echo "== mode $mode dataflow cells 110"; XF_DATAFLOW_MODE=$mode $B --schedule dataflow --cells 110 --substeps-per-step 20
+  echo "== mode $mode dataflow cells 28"; $B --schedule dataflow --cells 28 --substeps-per-step 20
+  echo "== dataflow cells 16"; $B --schedule dataflow --cells 16 --substeps-per-step 20
+  echo "== dataflow cells 70"; $B --schedule dataflow --cells 70 --substeps-per-step 20
 done
 } > gpurun_out/df_sweep.log 2>&1
-grep -o '^== .*\|"value": [0-9.e+]*\|"ms_per_step": [0-9.]*\|passed\|failed\|error' gpurun_out/df_sweep.log | grep -v '"value"' | head -80
+grep -o '^== .*\|"ms_per_step": [0-9.]*\|[0-9]* passed\|[0-9]* failed\|rror: .*' gpurun_out/df_sweep.log | cut -c1-150 | head -80

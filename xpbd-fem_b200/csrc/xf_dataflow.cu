@@ -39,16 +39,21 @@ constexpr uint32_t kVerMask = 0xffffff00u;
 // wait is a few polls.
 constexpr uint32_t kSpinLimit = 1u << 24;
 
+// Waiting is warp-uniform on purpose.  A lane that left a spin loop early would be parked at the loop's reconvergence
+// point, and independent thread scheduling releases parked lanes when the spinning ones yield (that is how it guarantees
+// progress): the warp would then run the ~750-instruction element body once per group of lanes.  Measured: 2x slower at
+// every mesh size.  With a vote over the lanes that have work, the warp leaves the loop as one.
 template <bool EXACT>
-__device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict, bool wait,
-                                               uint32_t expectTag, uint32_t newTag, uint32_t sleepNs) {
+__device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, unsigned mask, bool doPost, bool doPredict,
+                                               bool wait, uint32_t expectTag, uint32_t newTag, uint32_t sleepNs) {
 	VertexRegs v = LoadVertex(sc.Xw, i);
 	if (wait) {
-		uint32_t spins = 0;
-		while ((v.flags & kVerMask) != expectTag) {
-			if (++spins > kSpinLimit) { __trap(); }
+		for (uint32_t spins = 0;; spins++) {
+			const bool ok = (v.flags & kVerMask) == expectTag;
+			if (__all_sync(mask, ok)) { break; }
+			if (spins > kSpinLimit) { __trap(); }
 			if (sleepNs) { __nanosleep(sleepNs); }
-			v = LoadVertex(sc.Xw, i);
+			if (!ok) { v = LoadVertex(sc.Xw, i); }
 		}
 	}
 	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict);
@@ -56,10 +61,11 @@ __device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const Subs
 	StoreVertex(sc.Xw, i, v);
 }
 
-// One element: spin-gather the four versioned records, solve, scatter with this stage's tag.
-template <int ENERGY, bool SIMUL, bool EXACT, bool SENTINEL>
-__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t stageBase, uint32_t c,
-                                                uint32_t sleepNs) {
+// One element: spin-gather the four versioned records, solve, scatter with this stage's tag.  `mask` = the lanes of
+// this warp that run an element in this step (all of them call this function together).
+template <int ENERGY, bool SIMUL, bool EXACT>
+__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, unsigned mask, uint32_t stageBase,
+                                                uint32_t c, uint32_t sleepNs) {
 	const GlobalStore vs = StoreOf(sc);
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4];
@@ -68,36 +74,17 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 		vid[n] = raw[n] & 0x00ffffffu;
 		expectTag[n] = (stageBase + (raw[n] >> 24)) << 8;
 	}
-	// Polling is not free: a gather of 32 scattered records is up to 32 L1TEX wavefronts, the very resource the sweep is
-	// bound by.  So one lane polls ONE sentinel record (the corner whose previous writer is the latest stage) until it
-	// carries the expected tag (one wavefront per poll), and only then does the warp gather; stale records of the real
-	// gather are re-read lane by lane.
-	if (SENTINEL) {
-		const unsigned mask = __activemask();
-		if ((threadIdx.x & 31u) == (uint32_t)(__ffs(mask) - 1)) {
-			uint32_t bestRaw = raw[0];
-#pragma unroll
-			for (int n = 1; n < 4; n++) { bestRaw = (raw[n] >> 24) > (bestRaw >> 24) ? raw[n] : bestRaw; }
-			const uint32_t bestVid = bestRaw & 0x00ffffffu, bestTag = (stageBase + (bestRaw >> 24)) << 8;
-			for (uint32_t spins = 0;; spins++) {
-				if (spins > kSpinLimit) { __trap(); }
-				const VertexRegs sv = vs.LoadX(bestVid);
-				if ((sv.flags & kVerMask) == bestTag) { break; }
-				if (sleepNs) { __nanosleep(sleepNs); }
-			}
-		}
-		__syncwarp(mask);
-	}
 	VertexRegs v[4];
 #pragma unroll
 	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(vid[n]); }
 	for (uint32_t spins = 0;; spins++) {
-		if (spins > kSpinLimit) { __trap(); }
 		bool ok[4];
 #pragma unroll
 		for (int n = 0; n < 4; n++) { ok[n] = (v[n].flags & kVerMask) == expectTag[n]; }
-		if (ok[0] && ok[1] && ok[2] && ok[3]) { break; }
+		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
+		if (spins > kSpinLimit) { __trap(); }
 		if (sleepNs) { __nanosleep(sleepNs); }
+		// only the stale records are read again (a poll costs L1TEX wavefronts, the resource the sweep runs on)
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
 			if (!ok[n]) { v[n] = vs.LoadX(vid[n]); }
@@ -121,40 +108,52 @@ __device__ __forceinline__ void DataflowLoad(const DeviceScene& sc, uint32_t e, 
 
 template <int ENERGY, bool SIMUL, bool EXACT>
 __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
-                                                              uint32_t verBase, uint32_t sleepNs) {
-	const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x;
+                                                              uint32_t verBase, uint32_t tuning) {
+	const uint32_t lane = threadIdx.x & 31u;
 	const uint32_t gsize = gridDim.x * blockDim.x;
-	const uint32_t slot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
+	// work is dealt in warp-sized chunks round-robin over the CTAs (chunk k -> CTA k % grid, warp k / grid)
+	const uint32_t warpSlot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
 	const uint32_t nC = p.nColors;
 	const uint32_t stride = nC + 1u;
-	const uint32_t elemSleepNs = sleepNs >> 16; // packed: low 16 bits vertex-phase back-off, high 16 bits element back-off
-	sleepNs &= 0xffffu;
+	// packed tuning word: bits 0-15 vertex-phase back-off (ns), bits 16-31 element back-off (ns)
+	const uint32_t sleepNs = tuning & 0xffffu, elemSleepNs = tuning >> 16;
 	ElemRec rec;
-	for (uint32_t s = 0; s < nSubsteps; s++) {
+	for (uint32_t s = 0; s <= nSubsteps; s++) {
+		const bool closing = s == nSubsteps; // closing post phase (locks, manipulator, velocities) of the last substep
 		const uint32_t stageBase = verBase + s * stride;
-		if (p.colorStart[0] + slot < p.colorStart[1]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[0] + slot, rec); }
+		if (!closing && p.colorStart[0] + warpSlot + lane < p.colorStart[1]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[0] + warpSlot + lane, rec); }
 		// vertex phase: post of the previous substep + predict, once the vertex's last element of that substep has written
-		for (uint32_t i = gtid; i < sc.nV; i += gsize) {
-			const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-			DataflowVertex<EXACT>(sc, p, i, s > 0, true, s > 0, expectTag, stageBase << 8, sleepNs);
+		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) { // warp-uniform trip count
+			const uint32_t i = i0 + lane;
+			const bool has = i < sc.nV;
+			const unsigned mask = __ballot_sync(0xffffffffu, has);
+			if (has) {
+				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+			}
 		}
+		if (closing) { break; }
 		for (uint32_t c = 0; c < nC; c++) {
 			const uint32_t end = p.colorStart[c + 1];
-			uint32_t e = p.colorStart[c] + slot;
-			if (e < end) { DataflowElement<ENERGY, SIMUL, EXACT, true>(sc, p, rec, stageBase, c, elemSleepNs); }
-			for (e += gsize; e < end; e += gsize) {
-				ElemRec more;
-				DataflowLoad<ENERGY, EXACT>(sc, e, more);
-				DataflowElement<ENERGY, SIMUL, EXACT, false>(sc, p, more, stageBase, c, elemSleepNs);
+			uint32_t e0 = p.colorStart[c] + warpSlot;
+			if (e0 < end) {
+				const bool has = e0 + lane < end;
+				const unsigned mask = __ballot_sync(0xffffffffu, has);
+				if (has) { DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, rec, mask, stageBase, c, elemSleepNs); }
 			}
-			if (c + 1 < nC && p.colorStart[c + 1] + slot < p.colorStart[c + 2]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + slot, rec); }
+			for (e0 += gsize; e0 < end; e0 += gsize) {
+				const bool has = e0 + lane < end;
+				const unsigned mask = __ballot_sync(0xffffffffu, has);
+				if (has) {
+					ElemRec more;
+					DataflowLoad<ENERGY, EXACT>(sc, e0 + lane, more);
+					DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, more, mask, stageBase, c, elemSleepNs);
+				}
+			}
+			if (c + 1 < nC && p.colorStart[c + 1] + warpSlot + lane < p.colorStart[c + 2]) {
+				DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + warpSlot + lane, rec);
+			}
 		}
-	}
-	// closing post phase (locks, manipulator, velocities) of the last substep
-	const uint32_t lastBase = verBase + (nSubsteps - 1u) * stride;
-	for (uint32_t i = gtid; i < sc.nV; i += gsize) {
-		const uint32_t expectTag = (lastBase + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-		DataflowVertex<EXACT>(sc, p, i, true, false, true, expectTag, (lastBase + stride) << 8, sleepNs);
 	}
 }
 
