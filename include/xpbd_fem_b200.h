@@ -265,6 +265,10 @@ int xf_part_get_halo(const xf_partition* part, uint32_t color, uint32_t peerSlot
 int xf_part_get_order(const xf_partition* part, uint32_t* fullOrder);
 int xf_part_get_global_color_start(const xf_partition* part, uint32_t* colorStart);
 int xf_part_get_initial(const xf_partition* part, float* w, uint8_t* flags);
+/* Barrier-free schedule (XF_SCHEDULE_DATAFLOW; AUTO picks it when every vertex has at most two copies): per local element
+ * 4 codes naming the previous writer of each corner in the global serial order (0 = the substep's vertex phase, 255 = the
+ * same for a shared vertex, else 1 + colour), per local vertex the code of its last writer. */
+int xf_part_get_dataflow_codes(const xf_partition* part, uint8_t* predCode4, uint8_t* lastCode, int* outOk);
 int xf_part_ipc_export(xf_partition* part, void* out128);
 int xf_part_ipc_connect(xf_partition* part, const void* allRanksBlobs);
 int xf_part_set_ground(xf_partition* part, int enabled, float y0, float friction);

@@ -55,6 +55,42 @@ def test_plan_is_consistent_across_ranks():
     assert list(parts[0].peers()) == [1] and list(parts[1].peers()) == [0, 2] and list(parts[2].peers()) == [1]
 
 
+def test_dataflow_stage_codes_chain_across_ranks():
+    """Barrier-free schedule: around every vertex the writers (vertex phase, then its elements in colour order, on
+    whichever rank) must name each other as predecessors, consistently on every rank that holds a copy."""
+    nodes, idx, hint = xf.GenerateTetBlock(9, 3, wonkiness=0.1)
+    world = 3
+    parts = [xf.GeoPartitionCuda(nodes, idx, world, r, device=-1, color_hint=hint) for r in range(world)]
+    tets = idx.reshape(-1, 5)[:, 1:]
+    colors = np.empty(len(tets), dtype=np.int64)
+    order = parts[0].get_order()
+    cs = parts[0].global_color_start()
+    for c in range(parts[0].nColors):
+        colors[order[cs[c]:cs[c + 1]]] = c
+    copies = np.zeros(nodes.size // 3, dtype=np.int64)
+    for p in parts:
+        copies[p.local_verts()] += 1
+    writers = {}  # global vertex -> list of (colour, pred code)
+    for p in parts:
+        pred, last, ok = p.dataflow_codes()
+        assert ok  # slabs: at most two copies of any vertex
+        elems, _ = p.local_elements()
+        l2g = p.local_verts()
+        for k, e in enumerate(elems):
+            for j in range(4):
+                writers.setdefault(int(tets[e, j]), []).append((int(colors[e]), int(pred[k, j])))
+        # last-writer code of every local copy = 1 + the highest colour around the vertex, over ALL ranks
+        for i, g in enumerate(l2g):
+            around = colors[np.any(tets == g, axis=1)]
+            assert last[i] == (1 + around.max() if len(around) else 0)
+    for g, ws in writers.items():
+        ws.sort()
+        first = 255 if copies[g] > 1 else 0
+        assert ws[0][1] == first
+        for (c0, _), (c1, p1) in zip(ws, ws[1:]):
+            assert c1 > c0 and p1 == 1 + c0
+
+
 @pytest.mark.parametrize("world,extra", [(2, []), (3, ["--energy", "4", "--poisson", "0.495"]), (2, ["--serial", "--energy", "3", "--no-hint"]),
                                          (2, ["--pattern", "1", "--energy", "5"])])
 def test_partitioned_emulation_matches_single_scene_oracle(world, extra):
@@ -72,7 +108,8 @@ def gpu_count():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("extra", [[], ["--serial", "--energy", "4", "--poisson", "0.4999"], ["--no-hint", "--energy", "5"],
-                                   ["--schedule", "persistent"], ["--schedule", "persistent", "--energy", "3", "--poisson", "0.45"]])
+                                   ["--schedule", "persistent"], ["--schedule", "persistent", "--energy", "3", "--poisson", "0.45"],
+                                   ["--schedule", "per_color"], ["--schedule", "per_color", "--energy", "5", "--no-hint"]])
 def test_partitioned_gpu_matches_oracle(extra):
     if gpu_count() < 2:
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")

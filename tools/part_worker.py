@@ -26,7 +26,7 @@ ap.add_argument("--substeps", type=int, default=12)
 ap.add_argument("--no-hint", action="store_true")
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--time-substeps", type=int, default=0)
-ap.add_argument("--schedule", choices=["persistent", "per_color"], default="per_color")
+ap.add_argument("--schedule", choices=["dataflow", "persistent", "per_color"], default="dataflow")
 a = ap.parse_args()
 xf = load_package()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -93,7 +93,7 @@ else:
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint,
-                               schedule=xf.SCHEDULE_PERSISTENT if a.schedule == "persistent" else xf.SCHEDULE_LAUNCH_PER_COLOR)
+                               schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[a.schedule])
     blob = torch.from_numpy(part.ipc_export()).cuda()
     allb = [torch.empty_like(blob) for _ in range(world)]
     dist.all_gather(allb, blob)

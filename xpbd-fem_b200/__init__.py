@@ -196,6 +196,7 @@ def lib():
     L.xf_part_get_order.argtypes = [vp, vp]
     L.xf_part_get_global_color_start.argtypes = [vp, vp]
     L.xf_part_get_initial.argtypes = [vp, vp, vp]
+    L.xf_part_get_dataflow_codes.argtypes = [vp, vp, vp, C.POINTER(C.c_int)]
     L.xf_part_ipc_export.argtypes = [vp, vp]
     L.xf_part_ipc_connect.argtypes = [vp, vp]
     L.xf_part_set_ground.argtypes = [vp, i32, f32, f32]
@@ -542,6 +543,13 @@ class GeoPartitionCuda:
         f = np.empty(self.nV, dtype=np.uint8)
         _check(lib().xf_part_get_initial(self._h, _vp(w), _vp(f)))
         return w, f
+
+    def dataflow_codes(self):
+        pred = np.empty((self.nT, 4), dtype=np.uint8)
+        last = np.empty(self.nV, dtype=np.uint8)
+        ok = C.c_int()
+        _check(lib().xf_part_get_dataflow_codes(self._h, _vp(pred), _vp(last), C.byref(ok)))
+        return pred, last, bool(ok.value)
 
     def ipc_export(self):
         b = np.zeros(self.IPC_BYTES, dtype=np.uint8)

@@ -270,7 +270,8 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		}
 		rc = UploadScene(s);
 		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
-		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env) & 0xffffu; }
+		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env) & 0x7fffu; }
+		if (getenv("XF_DATAFLOW_NO_PREFETCH")) { s->spinSleepNs |= 0x8000u; }
 		if (const char* env = getenv("XF_DATAFLOW_ESLEEP_NS")) { s->spinSleepNs |= ((uint32_t)atoi(env) & 0xffffu) << 16; }
 		if (s->schedule == XF_SCHEDULE_AUTO) { // BRICKS measured slower, see xf_bricks.cu
 			s->schedule = !s->cooperative ? XF_SCHEDULE_LAUNCH_PER_COLOR : (s->dataflowOk ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_PERSISTENT);

@@ -98,6 +98,17 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v);
 }
 
+// The record of the stage after next: pulled into L1 now (the planes are read with ld.global.nc, which allocates in L1),
+// so that the load issued right before it is needed costs an L1 hit instead of an L2 / HBM round trip in the
+// stage-to-stage dependence chain.
+template <int ENERGY, bool EXACT>
+__device__ __forceinline__ void DataflowPrefetch(const DeviceScene& sc, uint32_t e) {
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eAd + e));
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eB + e));
+	if (kPrefactored && EXACT) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eC + e)); }
+}
+
 template <int ENERGY, bool EXACT>
 __device__ __forceinline__ void DataflowLoad(const DeviceScene& sc, uint32_t e, ElemRec& rec) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
@@ -116,7 +127,8 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 	const uint32_t nC = p.nColors;
 	const uint32_t stride = nC + 1u;
 	// packed tuning word: bits 0-15 vertex-phase back-off (ns), bits 16-31 element back-off (ns)
-	const uint32_t sleepNs = tuning & 0xffffu, elemSleepNs = tuning >> 16;
+	const uint32_t sleepNs = tuning & 0x7fffu, elemSleepNs = tuning >> 16;
+	const bool prefetch = (tuning & 0x8000u) == 0;
 	ElemRec rec;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps; // closing post phase (locks, manipulator, velocities) of the last substep
@@ -152,6 +164,10 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 			}
 			if (c + 1 < nC && p.colorStart[c + 1] + warpSlot + lane < p.colorStart[c + 2]) {
 				DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + warpSlot + lane, rec);
+			}
+			if (prefetch) {
+				const uint32_t c2 = c + 2 < nC ? c + 2 : c + 2 - nC; // wraps into the next substep
+				if (p.colorStart[c2] + warpSlot + lane < p.colorStart[c2 + 1]) { DataflowPrefetch<ENERGY, EXACT>(sc, p.colorStart[c2] + warpSlot + lane); }
 			}
 		}
 	}

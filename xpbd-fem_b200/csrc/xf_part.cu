@@ -20,6 +20,7 @@
 #include "xf_dispatch.cuh"
 #include "xf_element.cuh"
 #include "xf_partition.h"
+#include "xf_phase.cuh"
 
 namespace xf {
 
@@ -41,6 +42,9 @@ struct PartDevice {
 	const uint32_t* colorStart;   // device copies for the persistent kernel
 	const uint32_t* ifaceEnd;
 	uint32_t nColors;
+	// barrier-free schedule: acknowledgement words, one per local vertex, written by the peer that holds the other copy
+	uint32_t* myAck;
+	uint32_t* peerAck[kMaxPeers];
 };
 
 __device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
@@ -253,6 +257,175 @@ __global__ void __launch_bounds__(256, 2) k_part_persistent(const __grid_constan
 	}
 }
 
+// ---- barrier-free variant (XF_SCHEDULE_DATAFLOW): versioned records across GPUs -----------------------------------
+// Same idea as xf_dataflow.cu: a vertex record carries the stage that wrote it and every writer waits until the record
+// carries its predecessor's stage.  Here a shared vertex has a copy on two ranks; an element writes BOTH copies (its
+// local one and, over NVLink, the peer's) with one 32-byte store each, and everybody polls only its LOCAL copy.  Around
+// one vertex the writers are totally ordered and each waits for its predecessor, so the stores to one copy are causally
+// ordered even though they come from two GPUs: no flags, no fences, no epochs on the element path.  The vertex phase is
+// computed on both copies (identical inputs -> identical bits, as in the other partitioned schedules); the first element
+// around a shared vertex in a substep (code 255) additionally waits for the peer's acknowledgement word, so that its
+// remote store cannot land before the peer has pushed its copy through the vertex phase.
+__device__ __forceinline__ VertexRegs LoadVertexSys(const VertexRec* Xw, uint32_t i) {
+	VertexRegs v;
+	double packed;
+	asm volatile("ld.relaxed.sys.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x[0]), "=d"(v.x[1]), "=d"(v.x[2]), "=d"(packed) : "l"(Xw + i) : "memory");
+	const long long bits = __double_as_longlong(packed);
+	v.w = __int_as_float((int)(bits & 0xffffffffll));
+	v.flags = (uint32_t)((unsigned long long)bits >> 32);
+	return v;
+}
+__device__ __forceinline__ void StoreVertexSys(VertexRec* Xw, uint32_t i, const VertexRegs& v) {
+	const long long bits = (long long)(((unsigned long long)v.flags << 32) | (unsigned long long)(uint32_t)__float_as_int(v.w));
+	asm volatile("st.relaxed.sys.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(Xw + i), "d"(v.x[0]), "d"(v.x[1]), "d"(v.x[2]), "d"(__longlong_as_double(bits)) : "memory");
+}
+__device__ __forceinline__ uint32_t LoadAckSys(const uint32_t* p) {
+	uint32_t v;
+	asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
+struct VersionedMirrorStore {
+	GlobalStore base;
+	const PartDevice* pd;
+	bool iface; // this element touches a shared vertex
+	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return LoadVertexSys(base.Xw, i); }
+	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const {
+		StoreVertexSys(base.Xw, i, v);
+		if (iface) {
+			const uint32_t b = __ldg(pd->shareStart + i), e = __ldg(pd->shareStart + i + 1);
+			for (uint32_t k = b; k < e; k++) { StoreVertexSys(pd->peerXw[__ldg(pd->shareSlot + k)], __ldg(pd->shareRemoteIdx + k), v); }
+		}
+	}
+	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { base.LoadO(i, o); }
+	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { base.LoadV(i, o); }
+	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const { base.StoreV(i, v); }
+};
+
+constexpr uint32_t kPartSpinLimit = 1u << 26; // polls before a rank gives up on a peer (tens of seconds)
+constexpr uint32_t kTagMask = 0xffffff00u;
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const SubstepParams& p, const ElemRec& rec, unsigned mask, bool iface,
+                                                    uint32_t stageBase, uint32_t c) {
+	const VersionedMirrorStore vs{ StoreOf(pd.local), &pd, iface };
+	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
+	uint32_t vid[4], expectTag[4];
+	bool needAck[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		vid[n] = raw[n] & 0x00ffffffu;
+		const uint32_t code = raw[n] >> 24;
+		needAck[n] = code == 255u;
+		expectTag[n] = (stageBase + (needAck[n] ? 0u : code)) << 8;
+	}
+	VertexRegs v[4];
+	bool ackOk[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		v[n] = vs.LoadX(vid[n]);
+		ackOk[n] = !needAck[n];
+	}
+	const uint32_t ackWant = stageBase & 0x00ffffffu;
+	for (uint32_t spins = 0;; spins++) {
+		bool ok[4];
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			if (!ackOk[n]) { ackOk[n] = LoadAckSys(pd.myAck + vid[n]) == ackWant; }
+			ok[n] = ackOk[n] && (v[n].flags & kTagMask) == expectTag[n];
+		}
+		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
+		if (spins > kPartSpinLimit) { atomicExch(pd.errorFlag, 1u); __trap(); }
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			if ((v[n].flags & kTagMask) != expectTag[n]) { v[n] = vs.LoadX(vid[n]); }
+		}
+	}
+	const uint32_t newTag = (stageBase + 1u + c) << 8;
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
+	ElemRec r = rec;
+	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v);
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
+                                                          uint32_t verBase) {
+	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	const DeviceScene& sc = pd.local;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t gsize = gridDim.x * blockDim.x;
+	const uint32_t warpSlot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
+	const uint32_t nC = pd.nColors;
+	const uint32_t stride = nC + 1u;
+	for (uint32_t s = 0; s <= nSubsteps; s++) {
+		const bool closing = s == nSubsteps;
+		const uint32_t stageBase = verBase + s * stride;
+		// vertex phase on every local copy
+		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
+			const uint32_t i = i0 + lane;
+			const bool has = i < sc.nV;
+			const unsigned mask = __ballot_sync(0xffffffffu, has);
+			if (has) {
+				VertexRegs v = LoadVertexSys(sc.Xw, i);
+				if (s > 0) {
+					const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+					for (uint32_t spins = 0;; spins++) {
+						const bool ok = (v.flags & kTagMask) == expectTag;
+						if (__all_sync(mask, ok)) { break; }
+						if (spins > kPartSpinLimit) { atomicExch(pd.errorFlag, 1u); __trap(); }
+						if (!ok) { v = LoadVertexSys(sc.Xw, i); }
+					}
+				}
+				VertexPhaseBody<EXACT>(sc, p, i, v, s > 0, !closing);
+				v.flags = (v.flags & 0xffu) | (stageBase << 8);
+				StoreVertexSys(sc.Xw, i, v);
+				const uint32_t b = __ldg(pd.shareStart + i), e = __ldg(pd.shareStart + i + 1);
+				if (b < e) { // tell the holder of the other copy that this copy is through the vertex phase of this stage
+					__threadfence_system(); // the record above must be in place before the peer's element may overwrite it
+					for (uint32_t k = b; k < e; k++) {
+						uint32_t* dst = pd.peerAck[__ldg(pd.shareSlot + k)] + __ldg(pd.shareRemoteIdx + k);
+						asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(dst), "r"(stageBase & 0x00ffffffu) : "memory");
+					}
+				}
+			}
+		}
+		if (closing) { break; }
+		for (uint32_t c = 0; c < nC; c++) {
+			const uint32_t begin = __ldg(pd.colorStart + c), mid = __ldg(pd.ifaceEnd + c), end = __ldg(pd.colorStart + c + 1);
+			for (uint32_t e0 = begin + warpSlot; e0 < end; e0 += gsize) {
+				const uint32_t e = e0 + lane;
+				const bool has = e < end;
+				const unsigned mask = __ballot_sync(0xffffffffu, has);
+				if (has) {
+					ElemRec rec;
+					LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
+					PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, e < mid, stageBase, c);
+				}
+			}
+		}
+	}
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct PartDataflowRunner {
+	static cudaError_t Run(const PartDevice& pd, const SubstepParams& p, uint32_t nSubsteps, uint32_t verBase, int smCount, cudaStream_t st,
+	                       uint64_t* launches) {
+		if (DAMPED) { return cudaErrorNotSupported; }
+		auto fn = k_part_dataflow<ENERGY, SIMUL, EXACT>;
+		int perSm = 0;
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, 0);
+		if (e != cudaSuccess) { return e; }
+		if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		const dim3 grid((unsigned)(std::min(perSm, 2) * smCount));
+		void* args[] = { (void*)&pd, (void*)&p, (void*)&nSubsteps, (void*)&verBase };
+		e = cudaLaunchCooperativeKernel((const void*)fn, grid, dim3(256), args, 0, st); // cooperative = co-resident CTAs
+		++*launches;
+		return e;
+	}
+};
+
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 struct PartPersistentRunner {
 	static cudaError_t Run(const PartDevice& pd, const SubstepParams& p, uint32_t nSubsteps, unsigned long long* epoch, int smCount, cudaStream_t st,
@@ -314,6 +487,7 @@ struct xf_partition {
 	bool ownStream = false;
 	bool connected = false;
 	unsigned long long epoch = 0;
+	uint32_t verBase = 1; // first stage tag of the next barrier-free launch (24 bits, wraps; identical on all ranks)
 	uint64_t launches = 0;
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
@@ -383,8 +557,19 @@ int UploadPart(xf_partition* P) {
 	P->dev.shareStart = P->dShareStart;
 	P->dev.shareSlot = P->dShareSlot;
 	P->dev.shareRemoteIdx = P->dShareRemote;
-	XFP_CUDA(cudaMalloc((void**)&P->dev.myFlags, sizeof(unsigned long long) * 64));
-	XFP_CUDA(cudaMemset(P->dev.myFlags, 0, sizeof(unsigned long long) * 64));
+	// flag words (64 x u64) followed by one acknowledgement word per local vertex: one allocation, one IPC handle
+	const size_t flagBytes = sizeof(unsigned long long) * 64 + sizeof(uint32_t) * std::max(nV, 1u);
+	XFP_CUDA(cudaMalloc((void**)&P->dev.myFlags, flagBytes));
+	XFP_CUDA(cudaMemset(P->dev.myFlags, 0, flagBytes));
+	P->dev.myAck = reinterpret_cast<uint32_t*>(P->dev.myFlags + 64);
+	if (pl.dataflowOk) {
+		std::vector<ElemRecA> ad = pk.a;
+		for (size_t k = 0; k < ad.size(); k++) {
+			for (int j = 0; j < 4; j++) { ad[k].idx[j] |= (uint32_t)pl.predCode[4 * k + j] << 24; }
+		}
+		XFP_CUDA(UploadVecP(&d.eAd, ad));
+		XFP_CUDA(UploadVecP(&d.lastCode, pl.lastCode));
+	}
 	XFP_CUDA(cudaMalloc((void**)&P->dev.doneCounter, 2 * sizeof(unsigned int)));
 	XFP_CUDA(cudaMemset(P->dev.doneCounter, 0, 2 * sizeof(unsigned int)));
 	P->dev.errorFlag = P->dev.doneCounter + 1;
@@ -432,8 +617,15 @@ int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_
 		// Measured on 2 x B200 (998 250 tets): launch-per-phase 312 us/substep, persistent 390-426 us/substep; both are
 		// bound by the cross-GPU release/acquire chain (system fence round trip + flag flight, ~10 us per phase), and the
 		// back-to-back launches overlap it slightly better.  AUTO therefore means one launch per phase here.
-		if (P->schedule == XF_SCHEDULE_AUTO || P->schedule == XF_SCHEDULE_BRICKS) { P->schedule = XF_SCHEDULE_LAUNCH_PER_COLOR; }
-		if (P->schedule == XF_SCHEDULE_PERSISTENT && !prop.cooperativeLaunch) { P->schedule = XF_SCHEDULE_LAUNCH_PER_COLOR; }
+		// The barrier-free schedule (versioned records mirrored by peer stores) removes that chain from the element path.
+		if (P->schedule == XF_SCHEDULE_AUTO || P->schedule == XF_SCHEDULE_BRICKS) {
+			P->schedule = (P->plan.dataflowOk && prop.cooperativeLaunch) ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_LAUNCH_PER_COLOR;
+		}
+		if (P->schedule == XF_SCHEDULE_DATAFLOW && !P->plan.dataflowOk) {
+			delete P;
+			return Fail(XF_ERR_UNSUPPORTED, "XF_SCHEDULE_DATAFLOW on a partitioned mesh needs at most two copies of every vertex, <= 253 colours and <= 2^24 local vertices");
+		}
+		if (P->schedule >= XF_SCHEDULE_PERSISTENT && !prop.cooperativeLaunch) { P->schedule = XF_SCHEDULE_LAUNCH_PER_COLOR; }
 		if (params->stream) { P->stream = (cudaStream_t)params->stream; }
 		else {
 			e = cudaStreamCreateWithFlags(&P->stream, cudaStreamNonBlocking);
@@ -455,7 +647,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eAd, d.lastCode, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
@@ -517,6 +709,16 @@ int xf_part_get_initial(const xf_partition* P, float* w, uint8_t* flags) { // lo
 	return XF_OK;
 }
 
+// Stage codes of the barrier-free schedule (xf_partition.h): 4 per local element, 1 per local vertex; returns whether the
+// job qualifies for it (the same verdict on every rank).
+int xf_part_get_dataflow_codes(const xf_partition* P, uint8_t* predCode4, uint8_t* lastCode, int* outOk) {
+	if (!P) { return Fail(XF_ERR_INVALID, "null argument"); }
+	if (predCode4) { memcpy(predCode4, P->plan.predCode.data(), P->plan.predCode.size()); }
+	if (lastCode) { memcpy(lastCode, P->plan.lastCode.data(), P->plan.lastCode.size()); }
+	if (outOk) { *outOk = P->plan.dataflowOk ? 1 : 0; }
+	return XF_OK;
+}
+
 int xf_part_ipc_export(xf_partition* P, void* out128) {
 	if (!P || !out128) { return Fail(XF_ERR_INVALID, "null argument"); }
 	if (P->device < 0) { return Fail(XF_ERR_CUDA, "host-only partition has no device memory"); }
@@ -544,6 +746,7 @@ int xf_part_ipc_connect(xf_partition* P, const void* allRanks) {
 		P->openedPeers.push_back(fl);
 		P->dev.peerXw[s] = (VertexRec*)xw;
 		P->dev.peerFlags[s] = (unsigned long long*)fl;
+		P->dev.peerAck[s] = reinterpret_cast<uint32_t*>((unsigned long long*)fl + 64);
 	}
 	P->connected = true;
 	return XF_OK;
@@ -574,7 +777,17 @@ int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n
 	p.groundY = P->groundY;
 	p.groundKeep = 1.0f - P->groundFriction;
 	p.handleCount = 0;
-	if (P->schedule == XF_SCHEDULE_PERSISTENT) {
+	if (P->schedule == XF_SCHEDULE_DATAFLOW) {
+		const uint32_t stride = P->dev.nColors + 1u;
+		const uint32_t maxPerLaunch = (0x00ffffffu - 2u) / stride;
+		for (uint32_t done = 0; done < n;) {
+			const uint32_t m = std::min(n - done, maxPerLaunch);
+			XFP_CUDA(DispatchConfig<PartDataflowRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, m, P->verBase,
+			                                            P->smCount, P->stream, &P->launches));
+			P->verBase = (P->verBase + m * stride + 1u) & 0x00ffffffu;
+			done += m;
+		}
+	} else if (P->schedule == XF_SCHEDULE_PERSISTENT) {
 		XFP_CUDA(DispatchConfig<PartPersistentRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, n, &P->epoch,
 		                                              P->smCount, P->stream, &P->launches));
 	} else {

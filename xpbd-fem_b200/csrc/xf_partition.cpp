@@ -115,6 +115,34 @@ int BuildPartition(const HostMesh& m, uint32_t nRanks, uint32_t rank, PartPlan* 
 			}
 		}
 	}
+	// 6. stage codes of the barrier-free schedule, from the global colour-major order
+	{
+		std::vector<uint8_t> last(m.nV, 0), pred(4 * (size_t)m.nT, 0);
+		for (uint32_t k = 0; k < m.nT; k++) {
+			const uint32_t e = m.order[k];
+			const uint8_t code = (uint8_t)std::min<uint32_t>(1u + m.color[e], 254u);
+			for (int j = 0; j < 4; j++) {
+				uint8_t& l = last[m.idx[4 * (size_t)e + j]];
+				pred[4 * (size_t)e + j] = l;
+				l = code;
+			}
+		}
+		p.predCode.resize(4 * p.elems.size());
+		for (size_t k = 0; k < p.elems.size(); k++) {
+			for (int j = 0; j < 4; j++) {
+				const uint32_t v = m.idx[4 * (size_t)p.elems[k] + j];
+				uint8_t c = pred[4 * (size_t)p.elems[k] + j];
+				if (c == 0 && mask[v] != me) { c = 255; }
+				p.predCode[4 * k + j] = c;
+			}
+		}
+		p.lastCode.resize(p.verts.size());
+		for (size_t i = 0; i < p.verts.size(); i++) { p.lastCode[i] = last[p.verts[i]]; }
+		// a property of the whole job (every rank must reach the same verdict): at most two copies of any vertex
+		p.dataflowOk = nColors <= 253;
+		for (uint32_t v = 0; v < m.nV; v++) { if (__builtin_popcountll(mask[v]) > 2) { p.dataflowOk = false; } }
+		for (uint32_t q = 0; q < nRanks; q++) { if (counters[q] > 0x01000000u) { p.dataflowOk = false; } }
+	}
 	p.sendStart.assign(1, 0);
 	p.recvStart.assign(1, 0);
 	p.sendVerts.clear();

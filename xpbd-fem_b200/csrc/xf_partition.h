@@ -19,6 +19,13 @@ struct PartPlan {
 	std::vector<uint32_t> shareRemoteIdx; //   local index of the vertex on that rank
 	std::vector<uint32_t> sendStart, sendVerts; // [(colour * nPeers + slot)] -> local vertex ids to send after the phase
 	std::vector<uint32_t> recvStart, recvVerts; // same shape: local vertex ids overwritten by that peer's phase
+	// barrier-free schedule (xf_part.cu: k_part_dataflow): who wrote a vertex last, in the GLOBAL serial order.
+	// predCode: 4 per local element - 0 = this substep's vertex phase, 255 = vertex phase of a SHARED vertex (the element
+	// must also see the peer's acknowledgement that its copy has been through the vertex phase), else 1 + colour of the
+	// previous element around the vertex (on whichever rank).  lastCode: per local vertex, 1 + colour of its last element
+	// (0 = none).  dataflowOk: every shared vertex has exactly one other copy and the codes fit a byte.
+	std::vector<uint8_t> predCode, lastCode;
+	bool dataflowOk = false;
 };
 
 int BuildPartition(const HostMesh& full, uint32_t nRanks, uint32_t rank, PartPlan* out, std::string* err);
