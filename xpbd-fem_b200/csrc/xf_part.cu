@@ -13,6 +13,7 @@
 #include <cooperative_groups.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -45,6 +46,11 @@ struct PartDevice {
 	// barrier-free schedule: acknowledgement words, one per local vertex, written by the peer that holds the other copy
 	uint32_t* myAck;
 	uint32_t* peerAck[kMaxPeers];
+	// ... and its two warp pools: `nIfaceWarps` warps do nothing but the interface elements and the shared vertices (the
+	// work whose dependence chain crosses NVLink), the others the interior elements and the private vertices
+	const uint32_t* sharedList; // local ids of the shared vertices
+	const uint32_t* privList;   // local ids of the others
+	uint32_t nSharedList, nPrivList, nIfaceWarps;
 };
 
 __device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
@@ -285,17 +291,21 @@ __device__ __forceinline__ uint32_t LoadAckSys(const uint32_t* p) {
 	return v;
 }
 
+// Order of the two stores of a shared vertex: the PEER's copy first, then the local one.  The next writer around the
+// vertex may sit on this same rank; it starts when it sees the local record and will then store to the same peer
+// address from another SM.  Its store must not overtake ours on the way to the peer, so ours has to be on its way
+// before the local record can be seen - and its address is resolved before the solve (`remote`), not between the
+// two stores.  (Measured: with local-first stores and the address looked up in between, >= 4M-tet meshes lost
+// updates under load; a lost update is fail-stop - the tag never matches and the kernel traps - never a wrong result.)
 struct VersionedMirrorStore {
 	GlobalStore base;
-	const PartDevice* pd;
-	bool iface; // this element touches a shared vertex
+	uint32_t vid[4];
+	VertexRec* remote[4]; // the peer's copy of corner n, or nullptr
 	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return LoadVertexSys(base.Xw, i); }
 	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const {
+		VertexRec* r = i == vid[0] ? remote[0] : (i == vid[1] ? remote[1] : (i == vid[2] ? remote[2] : remote[3]));
+		if (r) { StoreVertexSys(r, 0, v); }
 		StoreVertexSys(base.Xw, i, v);
-		if (iface) {
-			const uint32_t b = __ldg(pd->shareStart + i), e = __ldg(pd->shareStart + i + 1);
-			for (uint32_t k = b; k < e; k++) { StoreVertexSys(pd->peerXw[__ldg(pd->shareSlot + k)], __ldg(pd->shareRemoteIdx + k), v); }
-		}
 	}
 	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { base.LoadO(i, o); }
 	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { base.LoadV(i, o); }
@@ -308,16 +318,23 @@ constexpr uint32_t kTagMask = 0xffffff00u;
 template <int ENERGY, bool SIMUL, bool EXACT>
 __device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const SubstepParams& p, const ElemRec& rec, unsigned mask, bool iface,
                                                     uint32_t stageBase, uint32_t c) {
-	const VersionedMirrorStore vs{ StoreOf(pd.local), &pd, iface };
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4];
 	bool needAck[4];
+	VersionedMirrorStore vs;
+	vs.base = StoreOf(pd.local);
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
 		vid[n] = raw[n] & 0x00ffffffu;
 		const uint32_t code = raw[n] >> 24;
 		needAck[n] = code == 255u;
 		expectTag[n] = (stageBase + (needAck[n] ? 0u : code)) << 8;
+		vs.vid[n] = vid[n];
+		vs.remote[n] = nullptr;
+		if (iface) { // at most one other copy (PartPlan::dataflowOk)
+			const uint32_t b = __ldg(pd.shareStart + vid[n]), e = __ldg(pd.shareStart + vid[n] + 1);
+			if (b < e) { vs.remote[n] = pd.peerXw[__ldg(pd.shareSlot + b)] + __ldg(pd.shareRemoteIdx + b); }
+		}
 	}
 	VertexRegs v[4];
 	bool ackOk[4];
@@ -355,19 +372,28 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
 	const DeviceScene& sc = pd.local;
 	const uint32_t lane = threadIdx.x & 31u;
-	const uint32_t gsize = gridDim.x * blockDim.x;
-	const uint32_t warpSlot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
+	// Two warp pools (global warp id = round-robin over the CTAs).  The cross-GPU dependence chain runs through the
+	// interface elements and the shared vertices: stage c on this rank waits for stage c-1 on the peer plus one NVLink
+	// flight.  If the warps that carry it also had interior work queued in front of it, every stage of that chain would
+	// wait for a whole local stage (measured: 8M tets on 2 GPUs no faster than on 1).  So a few warps carry nothing else.
+	const uint32_t gw = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;
+	const uint32_t nW = gridDim.x * (blockDim.x >> 5);
+	const uint32_t nI = min(pd.nIfaceWarps, nW / 2u);
+	const bool ifacePool = gw < nI;
+	const uint32_t poolSlot = (ifacePool ? gw : gw - nI) * 32u, poolStride = (ifacePool ? nI : nW - nI) * 32u;
+	const uint32_t* vertList = ifacePool ? pd.sharedList : pd.privList;
+	const uint32_t nVertList = ifacePool ? pd.nSharedList : pd.nPrivList;
 	const uint32_t nC = pd.nColors;
 	const uint32_t stride = nC + 1u;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps;
 		const uint32_t stageBase = verBase + s * stride;
 		// vertex phase on every local copy
-		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
-			const uint32_t i = i0 + lane;
-			const bool has = i < sc.nV;
+		for (uint32_t k0 = poolSlot; k0 < nVertList; k0 += poolStride) {
+			const bool has = k0 + lane < nVertList;
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
+				const uint32_t i = __ldg(vertList + k0 + lane);
 				VertexRegs v = LoadVertexSys(sc.Xw, i);
 				if (s > 0) {
 					const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
@@ -393,15 +419,16 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 		}
 		if (closing) { break; }
 		for (uint32_t c = 0; c < nC; c++) {
-			const uint32_t begin = __ldg(pd.colorStart + c), mid = __ldg(pd.ifaceEnd + c), end = __ldg(pd.colorStart + c + 1);
-			for (uint32_t e0 = begin + warpSlot; e0 < end; e0 += gsize) {
+			const uint32_t mid = __ldg(pd.ifaceEnd + c);
+			const uint32_t begin = ifacePool ? __ldg(pd.colorStart + c) : mid, end = ifacePool ? mid : __ldg(pd.colorStart + c + 1);
+			for (uint32_t e0 = begin + poolSlot; e0 < end; e0 += poolStride) {
 				const uint32_t e = e0 + lane;
 				const bool has = e < end;
 				const unsigned mask = __ballot_sync(0xffffffffu, has);
 				if (has) {
 					ElemRec rec;
 					LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
-					PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, e < mid, stageBase, c);
+					PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, ifacePool, stageBase, c);
 				}
 			}
 		}
@@ -498,6 +525,8 @@ struct xf_partition {
 	uint32_t* dShareStart = nullptr;
 	uint32_t* dShareSlot = nullptr;
 	uint32_t* dShareRemote = nullptr;
+	uint32_t* dSharedList = nullptr;
+	uint32_t* dPrivList = nullptr;
 	double* dPackX = nullptr;
 	double* dPackV = nullptr;
 	float* dPackW = nullptr;
@@ -563,6 +592,20 @@ int UploadPart(xf_partition* P) {
 	XFP_CUDA(cudaMemset(P->dev.myFlags, 0, flagBytes));
 	P->dev.myAck = reinterpret_cast<uint32_t*>(P->dev.myFlags + 64);
 	if (pl.dataflowOk) {
+		std::vector<uint32_t> sharedList, privList;
+		for (uint32_t i = 0; i < nV; i++) { (pl.shareStart[i + 1] > pl.shareStart[i] ? sharedList : privList).push_back(i); }
+		uint32_t maxIface = 0;
+		for (size_t c = 0; c + 1 < pl.colorStart.size(); c++) { maxIface = std::max(maxIface, pl.ifaceEnd[c] - pl.colorStart[c]); }
+		XFP_CUDA(UploadVecP(&P->dSharedList, sharedList));
+		XFP_CUDA(UploadVecP(&P->dPrivList, privList));
+		P->dev.sharedList = P->dSharedList;
+		P->dev.privList = P->dPrivList;
+		P->dev.nSharedList = (uint32_t)sharedList.size();
+		P->dev.nPrivList = (uint32_t)privList.size();
+		// one warp per interface chunk of the largest colour, and enough of them for the shared vertices' phase
+		P->dev.nIfaceWarps = pl.peers.empty() ? 0u : std::max((maxIface + 31u) / 32u, ((uint32_t)sharedList.size() + 63u) / 64u);
+		if (const char* env = getenv("XF_PART_IFACE_WARPS")) { P->dev.nIfaceWarps = (uint32_t)atoi(env); }
+		if (!sharedList.empty()) { P->dev.nIfaceWarps = std::max(P->dev.nIfaceWarps, 1u); } // somebody must carry the interface
 		std::vector<ElemRecA> ad = pk.a;
 		for (size_t k = 0; k < ad.size(); k++) {
 			for (int j = 0; j < 4; j++) { ad[k].idx[j] |= (uint32_t)pl.predCode[4 * k + j] << 24; }
@@ -647,7 +690,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eAd, d.lastCode, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eAd, d.lastCode, P->dSharedList, P->dPrivList, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
