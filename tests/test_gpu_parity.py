@@ -26,10 +26,11 @@ def settings_pair(**kw):
     return xf.make_settings(**kw), ob.make_settings(**kw)
 
 
-def make_pair(width=6, height=3, wonk=0.3, pattern=0, use_hint=True, precision=None, schedule=xf.SCHEDULE_PERSISTENT, density=1.0):
+def make_pair(width=6, height=3, wonk=0.3, pattern=0, use_hint=True, precision=None, schedule=xf.SCHEDULE_PERSISTENT, density=1.0,
+              grouping=xf.GROUPING_AUTO):
     nodes, idx, hint = xf.GenerateTetBlock(width, height, wonkiness=wonk, pattern=pattern)
     geo = xf.GeoLinear3dCuda(nodes, idx, density=density, precision=xf.PRECISION_EXACT if precision is None else precision,
-                             schedule=schedule, color_hint=hint if (use_hint and pattern == 0) else None)
+                             schedule=schedule, color_hint=hint if (use_hint and pattern == 0) else None, grouping=grouping)
     orc = ob.OracleScene(nodes, idx, density)
     orc.set_order(geo.get_order())
     return geo, orc
@@ -57,6 +58,21 @@ def test_exact_substeps_bit_identical(energy, sim, nu, schedule):
     geo, orc = make_pair(schedule=schedule)
     st, ost = settings_pair(energy=energy, simultaneous=sim, poisson=nu)
     for n in (1, 9, 30):  # several calls: exercises the call-boundary post/predict split
+        geo.Substep(st, DT, n)
+        orc.substep(ost, DT, n)
+        assert_bit_exact(geo, orc)
+    assert geo.CalculateVolume() == orc.volume()
+
+
+@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR])
+@pytest.mark.parametrize("energy,sim,nu,pattern", [(7, True, 0.5, 0), (4, False, 0.4999, 0), (5, True, 0.495, 1), (3, False, 0.5, 0)])
+def test_exact_clustered_coloring_bit_identical(energy, sim, nu, pattern, schedule):
+    """XF_GROUPING_CLUSTERS: one thread solves the six tets of a cell back to back on the barrier-free schedule
+    (k_substeps_cluster); for the other schedules the same serial order is an ordinary 48-colouring."""
+    geo, orc = make_pair(7, 4, 0.25, pattern=pattern, schedule=schedule, grouping=xf.GROUPING_CLUSTERS)
+    assert geo.nColors % 6 == 0
+    st, ost = settings_pair(energy=energy, simultaneous=sim, poisson=nu)
+    for n in (1, 2, 25):
         geo.Substep(st, DT, n)
         orc.substep(ost, DT, n)
         assert_bit_exact(geo, orc)

@@ -111,6 +111,31 @@ def test_lattice_hint_gives_24_balanced_colors():
     assert info["minColorSize"] == info["maxColorSize"] == 8 * 8 * 8 * 6 // 24
 
 
+@pytest.mark.parametrize("dims,pattern,wonk", [((8, 8), 0, 0.0), ((5, 3), 0, 0.2), ((6, 4), 1, 0.1)])
+def test_clustered_coloring(dims, pattern, wonk):
+    """Clustered colouring (one thread per cluster on the barrier-free schedule): still an ordinary conflict-free
+    colouring, colours in groups of 6 on MeshGen blocks (the six tets of a cell), 8 cluster colours on the uniform lattice,
+    and inside a colour group position t of cluster k sits at index k of colour C*6 + t."""
+    nodes, idx, hint = xf.GenerateTetBlock(*dims, pattern=pattern, wonkiness=wonk)
+    g = host_scene(nodes, idx, grouping=xf.GROUPING_CLUSTERS, color_hint=hint if pattern == 0 else None)
+    tets = idx.reshape(-1, 5)[:, 1:]
+    colors, order = g.get_colors(), g.get_order()
+    assert g.nColors % 6 == 0 and (pattern != 0 or g.nColors == 48)
+    for c in range(g.nColors):
+        verts = tets[colors == c].reshape(-1)
+        assert len(np.unique(verts)) == len(verts)
+    assert np.array_equal(np.sort(order), np.arange(len(tets)))
+    assert np.all(np.diff(colors[order].astype(np.int64)) >= 0)        # colour-major
+    sizes = np.bincount(colors, minlength=g.nColors)
+    start = np.concatenate([[0], np.cumsum(sizes)])
+    for C in range(g.nColors // 6):
+        assert len(set(sizes[6 * C:6 * C + 6])) == 1                    # every cell has six tets
+        cells = [order[start[6 * C + t]:start[6 * C + t + 1]] // 6 for t in range(6)]
+        for t in range(1, 6):
+            assert np.array_equal(cells[0], cells[t])                   # index k of every position = the same cell
+        assert np.array_equal(order[start[6 * C]:start[6 * C + 1]] % 6, np.zeros(sizes[6 * C]))  # position 0 = first tet of the cell
+
+
 def test_bad_color_hint_is_rejected():
     nodes, idx, hint = xf.GenerateTetBlock(3, 3)
     bad = hint.copy()

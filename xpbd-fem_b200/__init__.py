@@ -21,6 +21,7 @@ LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem
 XF_ABI_VERSION = 1
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
 PRECISION_EXACT, PRECISION_FAST = 0, 1
+GROUPING_AUTO, GROUPING_ELEMENTS, GROUPING_CLUSTERS = 0, 1, 2
 SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT, SCHEDULE_BRICKS, SCHEDULE_DATAFLOW = 0, 1, 2, 3, 4
 
 # flag word (Settings.h:9-75)
@@ -67,7 +68,7 @@ class CreateParams(C.Structure):
     _fields_ = [
         ("abiVersion", C.c_uint32), ("device", C.c_int32), ("density", C.c_float), ("autoResize", C.c_int32),
         ("precision", C.c_int32), ("schedule", C.c_int32), ("stream", C.c_void_p), ("colorHint", C.c_void_p),
-        ("colorHintCount", C.c_uint32), ("_reserved", C.c_uint32 * 5),
+        ("colorHintCount", C.c_uint32), ("grouping", C.c_uint32), ("_reserved", C.c_uint32 * 4),
     ]
 
 
@@ -127,7 +128,7 @@ EXPORTS = [
     "xf_part_create", "xf_part_destroy", "xf_part_local_vert_count", "xf_part_local_element_count", "xf_part_peer_count",
     "xf_part_color_count", "xf_part_global_vert_count", "xf_part_global_element_count", "xf_part_get_local_verts",
     "xf_part_get_local_elements", "xf_part_get_peers", "xf_part_get_halo", "xf_part_get_order", "xf_part_get_global_color_start",
-    "xf_part_get_initial", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
+    "xf_part_get_initial", "xf_part_get_dataflow_codes", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
     "xf_part_get_state", "xf_part_get_info",
 ]
 
@@ -246,7 +247,7 @@ class GeoLinear3dCuda:
     """One tet mesh resident on a B200; the drop-in for the reference's GeoLinear3d on the Substep path."""
 
     def __init__(self, nodes, idx_stream, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
-                 schedule=SCHEDULE_AUTO, color_hint=None, stream=None):
+                 schedule=SCHEDULE_AUTO, color_hint=None, stream=None, grouping=GROUPING_AUTO):
         L = lib()
         nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
         idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
@@ -257,6 +258,7 @@ class GeoLinear3dCuda:
         p.autoResize = 1 if auto_resize else 0
         p.precision = precision
         p.schedule = schedule
+        p.grouping = grouping
         p.stream = stream
         if color_hint is not None:
             color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)

@@ -55,7 +55,7 @@ struct xf_scene {
 	std::map<uint32_t, LaunchShape> shapes; // per energy
 	bool dataflowOk = false;  // stage codes fit the vertex-index top byte / the 24-bit record tag
 	uint32_t verBase = 1;     // first stage tag of the next dataflow launch (24-bit, wraps)
-	uint32_t spinSleepNs = 0; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
+	uint32_t spinSleepNs = 400; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
 	std::vector<uint32_t> intOfExt, extOfInt; // caller's vertex id <-> device vertex id
 	int smCount = 0;
 	size_t l2Bytes = 0;
@@ -79,7 +79,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -163,6 +163,12 @@ int UploadScene(xf_scene* s) {
 		}
 		XF_CUDA(Upload(&d.eAd, ad));
 		XF_CUDA(Upload(&d.lastCode, lastCode));
+		if (m.groupSize > 1) { // clustered colouring: slot / first / last bits of every corner, device order
+			std::vector<uint32_t> ek(m.nT);
+			for (uint32_t k = 0; k < m.nT; k++) { ek[k] = m.clusterInfo[bp.deviceOrder[k]]; }
+			XF_CUDA(Upload(&d.eK, ek));
+			d.groupSize = m.groupSize;
+		}
 	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
 	if (bricks) {
@@ -246,8 +252,12 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 	xf_scene* s = new (std::nothrow) xf_scene();
 	if (!s) { return Fail(XF_ERR_NOMEM, "out of host memory"); }
 	std::string err;
+	// clustered colouring (one thread per cluster of elements, xf_dataflow.cu): opt-in.  Measured on B200: 83 us per substep at
+	// 1M tets against 53 us with one thread per element (the chain is ~1.2 us of dependent arithmetic per element, not the L2
+	// hand-off, so serialising six elements in a thread lengthens it), 99 against 113 us at 2M tets.
+	const bool clustered = params->grouping == XF_GROUPING_CLUSTERS || (params->grouping == XF_GROUPING_AUTO && getenv("XF_CLUSTERS") != nullptr);
 	int rc = PrepareMesh(nodeXYZ, nodeFloatCount, idxStream, idxCount, params->density, params->autoResize != 0, params->colorHint,
-	                     params->colorHintCount, &s->mesh, &err);
+	                     params->colorHintCount, &s->mesh, &err, clustered);
 	if (rc != XF_OK) { delete s; return Fail(rc, err); }
 	s->precision = params->precision;
 	s->schedule = params->schedule;
@@ -340,7 +350,11 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 		for (uint32_t done = 0; done < n;) {
 			const uint32_t m = std::min(n - done, maxPerLaunch);
 			p.tickId = st->tickId + done;
-			XF_CUDA(LaunchSubstepsDataflow(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
+			if (s->dev.groupSize > 1) {
+				XF_CUDA(LaunchSubstepsCluster(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
+			} else {
+				XF_CUDA(LaunchSubstepsDataflow(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
+			}
 			s->verBase = (s->verBase + m * stride + 1u) & 0x00ffffffu;
 			done += m;
 		}

@@ -77,6 +77,7 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 	VertexRegs v[4];
 #pragma unroll
 	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(vid[n]); }
+	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume); // two chained divisions, in the shadow of the gather
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll
@@ -95,7 +96,7 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
 	ElemRec r = rec;
 	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
-	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v, ec);
 }
 
 // The record of the stage after next: pulled into L1 now (the planes are read with ld.global.nc, which allocates in L1),
@@ -171,6 +172,158 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 			}
 		}
 	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Clustered variant (HostMesh::groupSize > 1, see ColorClustered in xf_prepare.cpp): one thread solves the elements of
+// one cluster back to back.  The colours come in groups of G = groupSize; element k of colour C*G + t is the t-th
+// element of cluster k of cluster-colour C.  A vertex is gathered from L2 (waiting for its stage tag) at its FIRST use in
+// the cluster, lives in the thread's private shared-memory slots between uses, and is scattered - stamped with the stage
+// of the element that used it last, which is what every later reader expects - at its LAST use.  Dependences inside a
+// cluster never leave the thread; the chain through L2 has one link per cluster colour (8 on a MeshGen lattice)
+// instead of one per colour (24), and a vertex costs one gather and one scatter per cluster instead of per element.
+// ------------------------------------------------------------------------------------------------
+struct NoStore { // the clustered kernel routes the updated records itself
+	__device__ __forceinline__ void StoreX(uint32_t, const VertexRegs&) const {}
+	__device__ __forceinline__ void LoadO(uint32_t, double*) const {}
+	__device__ __forceinline__ void LoadV(uint32_t, double*) const {}
+	__device__ __forceinline__ void StoreV(uint32_t, const double*) const {}
+};
+
+constexpr int kClusterSlots = 8;
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__device__ __forceinline__ void ClusterElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, VertexRec* cache,
+                                               unsigned mask, uint32_t stageBase, uint32_t c) {
+	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
+	uint32_t vid[4], expectTag[4];
+	VertexRec* slot[4];
+	bool first[4], last[4];
+	VertexRegs v[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		vid[n] = raw[n] & 0x00ffffffu;
+		expectTag[n] = (stageBase + (raw[n] >> 24)) << 8;
+		const uint32_t bits = info >> (5 * n);
+		slot[n] = cache + (bits & 7u) * blockDim.x;
+		first[n] = (bits & 8u) != 0;
+		last[n] = (bits & 16u) != 0;
+		if (first[n]) {
+			v[n] = LoadVertex(sc.Xw, vid[n]);
+		} else {
+			const VertexRec r = *slot[n];
+			v[n].x[0] = r.x; v[n].x[1] = r.y; v[n].x[2] = r.z;
+			v[n].w = r.w;
+			v[n].flags = r.flags;
+		}
+	}
+	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	for (uint32_t spins = 0;; spins++) {
+		bool ok[4];
+#pragma unroll
+		for (int n = 0; n < 4; n++) { ok[n] = !first[n] || (v[n].flags & kVerMask) == expectTag[n]; }
+		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
+		if (spins > kSpinLimit) { __trap(); }
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			if (!ok[n]) { v[n] = LoadVertex(sc.Xw, vid[n]); }
+		}
+	}
+	const uint32_t newTag = (stageBase + 1u + c) << 8;
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
+	ElemRec r = rec;
+	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(NoStore{}, p, r, v, ec);
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		if (last[n]) {
+			StoreVertex(sc.Xw, vid[n], v[n]);
+		} else {
+			*slot[n] = VertexRec{ v[n].x[0], v[n].x[1], v[n].x[2], v[n].w, v[n].flags };
+		}
+	}
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_substeps_cluster(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
+                                                             uint32_t verBase, uint32_t tuning) {
+	extern __shared__ __align__(32) unsigned char clusterSmem[];
+	VertexRec* cache = reinterpret_cast<VertexRec*>(clusterSmem) + threadIdx.x; // slot s of this thread: cache[s * blockDim.x]
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t gsize = gridDim.x * blockDim.x;
+	const uint32_t warpSlot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
+	const uint32_t nC = p.nColors, G = sc.groupSize;
+	const uint32_t stride = nC + 1u;
+	const uint32_t sleepNs = tuning & 0x7fffu;
+	for (uint32_t s = 0; s <= nSubsteps; s++) {
+		const bool closing = s == nSubsteps;
+		const uint32_t stageBase = verBase + s * stride;
+		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
+			const uint32_t i = i0 + lane;
+			const bool has = i < sc.nV;
+			const unsigned mask = __ballot_sync(0xffffffffu, has);
+			if (has) {
+				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+			}
+		}
+		if (closing) { break; }
+		for (uint32_t c0 = 0; c0 < nC; c0 += G) {
+			const uint32_t n0 = p.colorStart[c0 + 1] - p.colorStart[c0]; // clusters of this cluster colour
+			for (uint32_t k0 = warpSlot; k0 < n0; k0 += gsize) {
+				// the records of this cluster (and of this thread's cluster of the next cluster colour) into L1
+				for (uint32_t t = 0; t < G; t++) {
+					const uint32_t e = p.colorStart[c0 + t] + k0 + lane;
+					if (e < p.colorStart[c0 + t + 1]) {
+						DataflowPrefetch<ENERGY, EXACT>(sc, e);
+						asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eK + e));
+					}
+				}
+				for (uint32_t t = 0; t < G; t++) {
+					const uint32_t c = c0 + t;
+					const uint32_t nt = p.colorStart[c + 1] - p.colorStart[c]; // clusters with more than t elements (sizes descend)
+					if (k0 >= nt) { break; }
+					const bool has = k0 + lane < nt;
+					const unsigned mask = __ballot_sync(0xffffffffu, has);
+					if (has) {
+						const uint32_t e = p.colorStart[c] + k0 + lane;
+						ElemRec rec;
+						DataflowLoad<ENERGY, EXACT>(sc, e, rec);
+						ClusterElement<ENERGY, SIMUL, EXACT>(sc, p, rec, __ldg(sc.eK + e), cache, mask, stageBase, c);
+					}
+				}
+			}
+		}
+	}
+}
+
+namespace {
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct ClusterRunner {
+	static cudaError_t Run(const DeviceScene& sc, const SubstepParams& p, uint32_t nSubsteps, int smCount, uint32_t verBase, uint32_t tuning,
+	                       cudaStream_t st, uint64_t* launches) {
+		auto fn = k_substeps_cluster<ENERGY, SIMUL, EXACT>;
+		const size_t smem = sizeof(VertexRec) * kClusterSlots * 256;
+		static int perSm = 0;
+		if (perSm == 0) {
+			cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+			if (e != cudaSuccess) { return e; }
+			e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, smem);
+			if (e != cudaSuccess) { return e; }
+			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		}
+		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&tuning };
+		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, smem, st);
+		++*launches;
+		return e;
+	}
+};
+}  // namespace
+
+cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                  uint32_t tuning, cudaStream_t stream, uint64_t* launchCount) {
+	return DispatchConfig<ClusterRunner>(p.energy, p.simultaneous != 0, exact, false, sc, p, nSubsteps, smCount, verBase, tuning, stream, launchCount);
 }
 
 namespace {

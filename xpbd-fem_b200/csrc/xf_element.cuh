@@ -292,9 +292,8 @@ __device__ __forceinline__ void Displacements(const VS& vs, const uint4& idx, co
 // EnergyXpbdConstrain, Xpbd.h:86-120.  Updates the register copies of the positions.
 template <bool EXACT, bool DAMPED, typename VS, typename PARAMS>
 __device__ __forceinline__ void ConstrainOne(const VS& vs, const PARAMS& p, const uint4& idx, VertexRegs (&v)[4], float U,
-                                             const float (&g)[4][3], float compliance, float dampingGamma) {
+                                             const float (&g)[4][3], float compliance, float alpha, float dampingGamma) {
 	typedef Op<EXACT> O;
-	float alpha = XF_DIV_MAYBE_ZERO(O, compliance, p.dt2);
 	float wgg = 1.0e-22f;
 #pragma unroll
 	for (int n = 0; n < 4; n++) { wgg = O::add(wgg, O::mul(v[n].w, O::dot(g[n], g[n]))); }
@@ -348,10 +347,8 @@ __device__ __forceinline__ void Cramer2(float A0, float A1, float A2, float b0, 
 template <bool EXACT, bool DAMPED, typename VS, typename PARAMS>
 __device__ __forceinline__ void ConstrainBoth(const VS& vs, const PARAMS& p, const uint4& idx, VertexRegs (&v)[4], float U0,
                                               float U1, const float (&g0)[4][3], const float (&g1)[4][3], float comp0, float comp1,
-                                              float dampingGamma) {
+                                              float alpha0, float alpha1, float dampingGamma) {
 	typedef Op<EXACT> O;
-	float alpha0 = O::div(comp0, p.dt2);
-	float alpha1 = XF_DIV_MAYBE_ZERO(O, comp1, p.dt2);
 	float w00 = 1.0e-22f, w10 = 1.0e-22f, w11 = 1.0e-22f;
 #pragma unroll
 	for (int n = 0; n < 4; n++) { w00 = O::add(w00, O::mul(v[n].w, O::dot(g0[n], g0[n]))); }
@@ -457,14 +454,29 @@ __device__ __forceinline__ void DeviatoricTerm(const ElemRec& e, const float (&P
 	}
 }
 
-// One element of GeoLinear3d::Constrain's main sweep.
+// comp = {1/mu/vol, 1/lambda/vol} (Fem.cpp:449) and, for the undamped solves, alpha = comp / dt^2 (Xpbd.h:88, 154): two
+// chained IEEE divisions that depend on the element record only.  The barrier-free kernels evaluate them BEFORE they wait
+// for the vertex records, so they are off the vertex-to-vertex dependence chain (same operations, same bits).
+struct ElemCompliance {
+	float comp0, comp1, alpha0, alpha1;
+};
+template <bool EXACT, typename PARAMS>
+__device__ __forceinline__ ElemCompliance ComplianceOf(const PARAMS& p, float volume) {
+	typedef Op<EXACT> O;
+	ElemCompliance c;
+	c.comp0 = O::div(p.invMu, volume);
+	c.comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, volume);
+	c.alpha0 = O::div(c.comp0, p.dt2);
+	c.alpha1 = XF_DIV_MAYBE_ZERO(O, c.comp1, p.dt2);
+	return c;
+}
+
 // One element of the main sweep with its four vertex records already in registers (`v` is updated and stored).
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
-__device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS& p, const ElemRec& e, VertexRegs (&v)[4]) {
+__device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS& p, const ElemRec& e, VertexRegs (&v)[4], const ElemCompliance& ec) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
-	float comp0 = O::div(p.invMu, e.volume);
-	float comp1 = XF_DIV_MAYBE_ZERO(O, p.invLambda, e.volume);
+	const float comp0 = ec.comp0, comp1 = ec.comp1;
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
 	float U0, U1;
 	bool haveF;
@@ -473,16 +485,20 @@ __device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS&
 	if (SIMUL) {
 		if (!(ENERGY == XF_ENERGY_MIXED || ENERGY == XF_ENERGY_YEOH_SKIN)) { DeformationGradient<EXACT>(e, P, F); }
 		U1 = VolumetricFromF<EXACT>(e, F, p.a, g1);
-		ConstrainBoth<EXACT, DAMPED>(vs, p, e.idx, v, U0, U1, g0, g1, comp0, comp1, p.damping);
+		ConstrainBoth<EXACT, DAMPED>(vs, p, e.idx, v, U0, U1, g0, g1, comp0, comp1, ec.alpha0, ec.alpha1, p.damping);
 	} else {
-		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U0, g0, comp0, p.damping);
+		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U0, g0, comp0, ec.alpha0, p.damping);
 		Edges<EXACT>(v, P);
 		DeformationGradient<EXACT>(e, P, F);
 		U1 = VolumetricFromF<EXACT>(e, F, p.a, g1);
-		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U1, g1, comp1, p.damping);
+		ConstrainOne<EXACT, DAMPED>(vs, p, e.idx, v, U1, g1, comp1, ec.alpha1, p.damping);
 	}
 #pragma unroll
 	for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
+}
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
+__device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS& p, const ElemRec& e, VertexRegs (&v)[4]) {
+	SolveElementGathered<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, e, v, ComplianceOf<EXACT>(p, e.volume));
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
@@ -508,7 +524,7 @@ __device__ __forceinline__ void SolveVolumeOnly(const VS& vs, const PARAMS& p, c
 	DeformationGradient<EXACT>(e, P, F);
 	// U = weight*(J-1)*(J-1) with weight == 1: (1*(J-1))*(J-1) == (J-1)^2
 	float U = VolumetricFromF<EXACT>(e, F, 1.0f, g);
-	ConstrainOne<EXACT, false>(vs, p, e.idx, v, U, g, comp, 0.0f);
+	ConstrainOne<EXACT, false>(vs, p, e.idx, v, U, g, comp, XF_DIV_MAYBE_ZERO(O, comp, p.dt2), 0.0f);
 #pragma unroll
 	for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
 }

@@ -344,6 +344,7 @@ __device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const 
 		ackOk[n] = !needAck[n];
 	}
 	const uint32_t ackWant = stageBase & 0x00ffffffu;
+	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll
@@ -363,7 +364,7 @@ __device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const 
 	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
 	ElemRec r = rec;
 	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
-	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v, ec);
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT>

@@ -186,8 +186,128 @@ int ColorGeneric(const std::vector<uint32_t>& idx, uint32_t nV, uint32_t nT, std
 
 }  // namespace
 
+// ------------------------------------------------------------------------------------------------
+// Clustered colouring.  The 24 (or more) elements around a vertex are mutually dependent, so a colour sweep is a chain of
+// >= 24 element latencies per substep, each paid through L2.  If ONE thread solves a small cluster of elements that share
+// vertices (MeshGen: the six Kuhn tets of a cell, 8 vertices) back to back, the dependences inside the cluster never
+// leave the thread, and only clusters need colouring (8 classes on the lattice).  As a serial order this is
+// (cluster colour, position in cluster, cluster), expressed for every other schedule as an ordinary colouring with
+// colour = clusterColour * groupSize + position: two elements of one such colour sit in different clusters of one
+// cluster colour, which share no vertex.
+// Clusters: consecutive stream elements while they stay connected and touch <= 8 distinct vertices.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr uint32_t kClusterVerts = 8, kClusterMaxElems = 8;
+
+bool ColorClustered(HostMesh& m) {
+	const uint32_t nT = m.nT;
+	std::vector<uint32_t> clusterStart; // offsets into the stream
+	{
+		uint32_t verts[kClusterVerts];
+		uint32_t nVerts = 0, count = 0;
+		for (uint32_t e = 0; e < nT; e++) {
+			const uint32_t* v = &m.idx[4 * (size_t)e];
+			uint32_t fresh = 0, shared = 0;
+			for (int j = 0; j < 4; j++) {
+				bool found = false;
+				for (uint32_t k = 0; k < nVerts; k++) { found = found || verts[k] == v[j]; }
+				if (found) { shared++; } else { fresh++; }
+			}
+			if (count == 0 || count >= kClusterMaxElems || shared == 0 || nVerts + fresh > kClusterVerts) {
+				clusterStart.push_back(e);
+				nVerts = 0;
+				count = 0;
+			}
+			for (int j = 0; j < 4; j++) {
+				bool found = false;
+				for (uint32_t k = 0; k < nVerts; k++) { found = found || verts[k] == v[j]; }
+				if (!found) { verts[nVerts++] = v[j]; }
+			}
+			count++;
+		}
+		clusterStart.push_back(nT);
+	}
+	const uint32_t nClusters = (uint32_t)clusterStart.size() - 1;
+	uint32_t G = 0;
+	for (uint32_t c = 0; c < nClusters; c++) { G = std::max(G, clusterStart[c + 1] - clusterStart[c]); }
+	if (G < 2) { return false; } // nothing to gain
+	// first-fit colouring of the clusters
+	std::vector<ColorSet> seen(m.nV);
+	std::vector<uint32_t> cColor(nClusters);
+	uint32_t nCC = 0;
+	for (uint32_t c = 0; c < nClusters; c++) {
+		ColorSet used;
+		for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) {
+			for (int j = 0; j < 4; j++) {
+				const ColorSet& s = seen[m.idx[4 * (size_t)e + j]];
+				for (int wd = 0; wd < kMaxColors / 64; wd++) { used.bits[wd] |= s.bits[wd]; }
+			}
+		}
+		int col = -1;
+		for (int wd = 0; wd < kMaxColors / 64 && col < 0; wd++) { if (~used.bits[wd]) { col = wd * 64 + __builtin_ctzll(~used.bits[wd]); } }
+		if (col < 0) { return false; }
+		cColor[c] = (uint32_t)col;
+		nCC = std::max(nCC, (uint32_t)col + 1);
+		for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) {
+			for (int j = 0; j < 4; j++) { seen[m.idx[4 * (size_t)e + j]].Add((uint32_t)col); }
+		}
+	}
+	if ((uint64_t)nCC * G > 254u) { return false; } // stage codes are bytes; ordinary colouring instead
+	// clusters of one colour: larger first, so that "cluster k" means the same thing at every position t
+	std::vector<uint32_t> byColor(nClusters);
+	std::iota(byColor.begin(), byColor.end(), 0u);
+	std::stable_sort(byColor.begin(), byColor.end(), [&](uint32_t a, uint32_t b) {
+		if (cColor[a] != cColor[b]) { return cColor[a] < cColor[b]; }
+		return clusterStart[a + 1] - clusterStart[a] > clusterStart[b + 1] - clusterStart[b];
+	});
+	const uint32_t nColors = nCC * G;
+	m.color.assign(nT, 0);
+	m.colorStart.assign(nColors + 1, 0);
+	for (uint32_t c = 0; c < nClusters; c++) {
+		for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) {
+			m.color[e] = cColor[c] * G + (e - clusterStart[c]);
+			m.colorStart[m.color[e] + 1]++;
+		}
+	}
+	for (uint32_t c = 0; c < nColors; c++) { m.colorStart[c + 1] += m.colorStart[c]; }
+	m.order.resize(nT);
+	{
+		std::vector<uint32_t> cursor(m.colorStart.begin(), m.colorStart.end() - 1);
+		for (uint32_t k = 0; k < nClusters; k++) { // clusters in (colour, size-descending) order fill every position in that order
+			const uint32_t c = byColor[k];
+			for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) { m.order[cursor[m.color[e]]++] = e; }
+		}
+	}
+	// slot / first / last bits
+	m.clusterInfo.assign(nT, 0);
+	for (uint32_t c = 0; c < nClusters; c++) {
+		uint32_t verts[kClusterVerts], lastElem[kClusterVerts];
+		uint32_t nVerts = 0;
+		for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) {
+			for (int j = 0; j < 4; j++) {
+				const uint32_t v = m.idx[4 * (size_t)e + j];
+				uint32_t slot = nVerts;
+				for (uint32_t k = 0; k < nVerts; k++) { if (verts[k] == v) { slot = k; } }
+				uint32_t bits = slot;
+				if (slot == nVerts) { verts[nVerts++] = v; bits |= 8u; }
+				lastElem[slot] = e;
+				m.clusterInfo[e] |= bits << (5 * j);
+			}
+		}
+		for (uint32_t e = clusterStart[c]; e < clusterStart[c + 1]; e++) {
+			for (int j = 0; j < 4; j++) {
+				const uint32_t slot = (m.clusterInfo[e] >> (5 * j)) & 7u;
+				if (lastElem[slot] == e) { m.clusterInfo[e] |= 16u << (5 * j); }
+			}
+		}
+	}
+	m.groupSize = G;
+	return true;
+}
+}  // namespace
+
 int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density, bool autoResize,
-                const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err) {
+                const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err, bool clustered) {
 	if (!nodeXYZ || !idxStream || idxCount == 0 || idxCount % 5 != 0 || nodeFloatCount % 3 != 0) {
 		*err = "mesh stream must be [4,v0,v1,v2,v3]* (CON_TET records, Connectivity.h:16) with xyz float triples";
 		return XF_ERR_INVALID;
@@ -252,6 +372,8 @@ int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* i
 	for (uint32_t i = 0; i < nV; i++) { m.w[i] = 1.0f / mass[i]; }
 
 	// colouring
+	if (clustered && ColorClustered(m)) { return XF_OK; }
+	m.groupSize = 0;
 	uint32_t nColors = 0;
 	bool hinted = false;
 	if (colorHint && colorHintCount == nT && colorHint[0] != 0xffffffffu) {

@@ -73,6 +73,9 @@ struct DeviceScene {
 	uint8_t* lastCode = nullptr;
 	// device vertex id -> caller's vertex id (nullptr = identity); used where state crosses the ABI
 	uint32_t* extOfInt = nullptr;
+	// clustered dataflow (k_substeps_cluster): per element the cluster slot / first / last bits of its corners
+	uint32_t* eK = nullptr;
+	uint32_t groupSize = 0;
 };
 
 constexpr int kMaxHandles = 64;
@@ -151,6 +154,12 @@ struct HostMesh {
 	std::vector<uint32_t> order;  // equivalent serial order (colour-major, index-minor)
 	std::vector<uint32_t> colorStart; // nColors + 1 offsets into `order`
 	float origin[3] = { 0.0f, 0.0f, 0.0f };
+	// clustered colouring (PrepareMesh with clusterVerts > 0): colours come in groups of `groupSize`; element k of colour
+	// C*groupSize + t is the t-th element of cluster k of cluster-colour C, and a cluster's elements touch at most 8
+	// distinct vertices.  clusterInfo (stream order): per corner n, bits [5n, 5n+5) = slot (3 bits) | first use in the
+	// cluster (bit 3) | last use in the cluster (bit 4).
+	uint32_t groupSize = 0;
+	std::vector<uint32_t> clusterInfo;
 };
 
 // Brick plan (xf_prepare.cpp): elements are grouped into `nBricks` spatially compact chunks (Morton order of the
@@ -170,7 +179,7 @@ void BuildBricks(const HostMesh& mesh, uint32_t nBricks, uint32_t slotCap, Brick
 
 // Returns 0 or an xf_status; on failure `err` holds the message.
 int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density,
-                bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err);
+                bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err, bool clustered = false);
 // Element planes for the elements `elems` (global ids, in device order); `localIdx` (4 per element) replaces the
 // mesh's vertex ids when the device uses a local vertex numbering (partitioned meshes), else nullptr.
 struct PackedElements {
@@ -195,6 +204,8 @@ cudaError_t LaunchSubstepsBricks(const DeviceScene& sc, const SubstepParams& p, 
                                  uint64_t* launchCount);
 cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                    uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount);
+cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                  uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
                                      cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchElementVolumes(const DeviceScene& sc, cudaStream_t stream, uint64_t* launchCount);  // -> sc.eScratch, stream order
