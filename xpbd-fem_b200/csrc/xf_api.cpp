@@ -57,7 +57,6 @@ struct xf_scene {
 	uint32_t verBase = 1;     // first stage tag of the next dataflow launch (24-bit, wraps)
 	uint32_t spinSleepNs = 400; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
 	std::vector<uint32_t> intOfExt, extOfInt; // caller's vertex id <-> device vertex id
-	bool usePairs = true;     // two warps per 32 elements where the pair kernel covers the settings (XF_NO_PAIRS disables)
 	int smCount = 0;
 	size_t l2Bytes = 0;
 	uint64_t launches = 0;
@@ -283,7 +282,6 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		if (rc != XF_OK) { FreeDevice(s); delete s; return rc; }
 		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env) & 0x7fffu; }
 		if (getenv("XF_DATAFLOW_NO_PREFETCH")) { s->spinSleepNs |= 0x8000u; }
-		if (getenv("XF_NO_PAIRS")) { s->usePairs = false; }
 		if (const char* env = getenv("XF_DATAFLOW_ESLEEP_NS")) { s->spinSleepNs |= ((uint32_t)atoi(env) & 0xffffu) << 16; }
 		if (s->schedule == XF_SCHEDULE_AUTO) { // BRICKS measured slower, see xf_bricks.cu
 			s->schedule = !s->cooperative ? XF_SCHEDULE_LAUNCH_PER_COLOR : (s->dataflowOk ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_PERSISTENT);
@@ -354,8 +352,6 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 			p.tickId = st->tickId + done;
 			if (s->dev.groupSize > 1) {
 				XF_CUDA(LaunchSubstepsCluster(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
-			} else if (s->usePairs && PairKernelCovers(p)) {
-				XF_CUDA(LaunchSubstepsPair(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			} else {
 				XF_CUDA(LaunchSubstepsDataflow(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			}

@@ -204,10 +204,6 @@ cudaError_t LaunchSubstepsBricks(const DeviceScene& sc, const SubstepParams& p, 
                                  uint64_t* launchCount);
 cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                    uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount);
-// two warps per 32 elements (xf_dataflow_pair.cu): prefactored energies, simultaneous solve, undamped
-bool PairKernelCovers(const SubstepParams& p);
-cudaError_t LaunchSubstepsPair(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
-                               uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                   uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
