@@ -173,6 +173,9 @@ uint32_t xf_color_count(const xf_scene* scene);
 int xf_get_order(const xf_scene* scene, uint32_t* order);
 int xf_get_colors(const xf_scene* scene, uint32_t* colorOfElement);
 /* Per-element constants as InitFiniteElement produced them (Fem.cpp:196-224); any pointer may be NULL. */
+/* Barrier-free schedule (XF_SCHEDULE_DATAFLOW): for the k-th element of xf_get_order, the stage code of the previous writer of
+ * each of its corners (0 = the substep's vertex phase, else 1 + colour); per vertex the code of its last writer (0 = none). */
+int xf_get_stage_codes(const xf_scene* scene, uint8_t* predCode4, uint8_t* lastCode);
 int xf_get_elements(const xf_scene* scene, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea);
 
 /* ---- stepping (Geo3d::Substep, Geo.cpp:305-356), n substeps with tickId advancing per substep ---- */

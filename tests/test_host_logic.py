@@ -136,6 +136,34 @@ def test_clustered_coloring(dims, pattern, wonk):
         assert np.array_equal(order[start[6 * C]:start[6 * C + 1]] % 6, np.zeros(sizes[6 * C]))  # position 0 = first tet of the cell
 
 
+@pytest.mark.parametrize("kind", ["lattice_hint", "lattice_generic", "mirrored", "clusters", "armadillo"])
+def test_stage_codes_replay(kind):
+    """Barrier-free schedule: replay the serial order with one stage tag per vertex.  Every element must find, on each of its
+    corners, exactly the tag its record expects (else the device would wait forever), and the vertex phase must find the
+    tag of the vertex's last writer."""
+    kw = {}
+    if kind == "armadillo":
+        if not ob.have_ref():
+            pytest.skip("needs the reference's embedded Armadillo tables")
+        nodes, idx = ob.RefScene.armadillo().get_mesh()
+        kw = dict(density=2.0, auto_resize=True)
+    else:
+        nodes, idx, hint = xf.GenerateTetBlock(7, 4, pattern=1 if kind == "mirrored" else 0, wonkiness=0.1)
+        if kind == "lattice_hint":
+            kw = dict(color_hint=hint)
+        if kind == "clusters":
+            kw = dict(grouping=xf.GROUPING_CLUSTERS)
+    g = host_scene(nodes, idx, **kw)
+    tets = idx.reshape(-1, 5)[:, 1:]
+    order, colors = g.get_order(), g.get_colors()
+    pred, last = g.stage_codes()
+    tag = np.zeros(g.nV, dtype=np.int64)          # 0 = written by the vertex phase
+    for k, e in enumerate(order):
+        assert np.array_equal(tag[tets[e]], pred[k]), "element %d would wait forever" % e
+        tag[tets[e]] = 1 + colors[e]
+    assert np.array_equal(tag, last)
+
+
 def test_bad_color_hint_is_rejected():
     nodes, idx, hint = xf.GenerateTetBlock(3, 3)
     bad = hint.copy()

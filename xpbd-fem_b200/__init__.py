@@ -118,7 +118,7 @@ _lib = None
 
 EXPORTS = [
     "xf_last_error", "xf_device_count", "xf_default_create_params", "xf_generate_tet_block", "xf_create", "xf_destroy",
-    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_elements", "xf_substep",
+    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_elements", "xf_substep",
     "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
     "xf_frame_state_init", "xf_frame_update",
@@ -154,6 +154,7 @@ def lib():
         getattr(L, n).restype = u32
     L.xf_get_order.argtypes = [vp, vp]
     L.xf_get_colors.argtypes = [vp, vp]
+    L.xf_get_stage_codes.argtypes = [vp, vp, vp]
     L.xf_get_elements.argtypes = [vp] * 7
     L.xf_substep.argtypes = [vp, vp, vp, f32, u32]
     L.xf_sync.argtypes = [vp]
@@ -318,6 +319,12 @@ class GeoLinear3dCuda:
         o = np.empty(self.nT, dtype=np.uint32)
         _check(lib().xf_get_order(self._h, _vp(o)))
         return o
+
+    def stage_codes(self):
+        pred = np.empty((self.nT, 4), dtype=np.uint8)
+        last = np.empty(self.nV, dtype=np.uint8)
+        _check(lib().xf_get_stage_codes(self._h, _vp(pred), _vp(last)))
+        return pred, last
 
     def get_colors(self):
         c = np.empty(self.nT, dtype=np.uint32)

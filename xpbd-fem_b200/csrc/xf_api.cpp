@@ -151,16 +151,13 @@ int UploadScene(xf_scene* s) {
 	// dataflow schedule: previous-writer stage code per (element, vertex) in the top byte of the index, last-writer code per vertex
 	s->dataflowOk = m.nV <= 0x01000000u && d.nColors <= 254u;
 	if (s->dataflowOk) {
-		std::vector<uint8_t> lastCode(m.nV, 0);
+		std::vector<uint8_t> pred, lastExt, lastCode(m.nV, 0);
+		StageCodes(m, bp.deviceOrder, &pred, &lastExt);
 		std::vector<ElemRecA> ad = pk.a;
-		for (uint32_t k = 0; k < m.nT; k++) { // device order is colour-major: a vertex's elements are met in colour order
-			const uint32_t code = 1u + m.color[bp.deviceOrder[k]];
-			for (int j = 0; j < 4; j++) {
-				const uint32_t v = pk.a[k].idx[j];
-				ad[k].idx[j] = v | ((uint32_t)lastCode[v] << 24);
-				lastCode[v] = (uint8_t)code;
-			}
+		for (uint32_t k = 0; k < m.nT; k++) {
+			for (int j = 0; j < 4; j++) { ad[k].idx[j] = pk.a[k].idx[j] | ((uint32_t)pred[4 * (size_t)k + j] << 24); }
 		}
+		for (uint32_t v = 0; v < m.nV; v++) { lastCode[s->intOfExt[v]] = lastExt[v]; }
 		XF_CUDA(Upload(&d.eAd, ad));
 		XF_CUDA(Upload(&d.lastCode, lastCode));
 		if (m.groupSize > 1) { // clustered colouring: slot / first / last bits of every corner, device order
@@ -321,6 +318,16 @@ int xf_get_colors(const xf_scene* s, uint32_t* colorOfElement) {
 	memcpy(colorOfElement, s->mesh.color.data(), sizeof(uint32_t) * s->mesh.nT);
 	return XF_OK;
 }
+int xf_get_stage_codes(const xf_scene* s, uint8_t* predCode4, uint8_t* lastCode) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	if (s->mesh.colorStart.size() - 1 > 254u) { return Fail(XF_ERR_UNSUPPORTED, "more than 254 colours: stage codes do not fit a byte"); }
+	std::vector<uint8_t> pred, last;
+	StageCodes(s->mesh, s->mesh.order, &pred, &last);
+	if (predCode4) { memcpy(predCode4, pred.data(), pred.size()); }
+	if (lastCode) { memcpy(lastCode, last.data(), last.size()); }
+	return XF_OK;
+}
+
 int xf_get_elements(const xf_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea) {
 	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
 	const HostMesh& m = s->mesh;

@@ -499,6 +499,20 @@ void BuildBricks(const HostMesh& m, uint32_t nBricks, uint32_t slotCap, BrickPla
 	}
 }
 
+void StageCodes(const HostMesh& m, const std::vector<uint32_t>& order, std::vector<uint8_t>* pred, std::vector<uint8_t>* last) {
+	pred->assign(4 * (size_t)m.nT, 0);
+	last->assign(m.nV, 0);
+	for (uint32_t k = 0; k < m.nT; k++) { // colour-major: the elements around a vertex are met in colour order
+		const uint32_t e = order[k];
+		const uint8_t code = (uint8_t)(1u + m.color[e]);
+		for (int j = 0; j < 4; j++) {
+			uint8_t& l = (*last)[m.idx[4 * (size_t)e + j]];
+			(*pred)[4 * (size_t)k + j] = l;
+			l = code;
+		}
+	}
+}
+
 void PackElements(const HostMesh& m, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out) {
 	const size_t n = elems.size();
 	out->a.resize(n);

@@ -188,6 +188,10 @@ struct PackedElements {
 	std::vector<float4> c;
 	std::vector<float> area;
 };
+// Stage codes of the barrier-free schedule for the elements in `order` (colour-major): pred = 4 per element, the code of the
+// previous writer of each corner (0 = the substep's vertex phase, else 1 + colour); last = per vertex (caller's numbering)
+// the code of its last writer.
+void StageCodes(const HostMesh& mesh, const std::vector<uint32_t>& order, std::vector<uint8_t>* pred, std::vector<uint8_t>* last);
 void PackElements(const HostMesh& mesh, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out);
 int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
                       std::string* err);
