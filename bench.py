@@ -44,6 +44,8 @@ def parse_args():
     ap.add_argument("--substeps-per-step", type=int, default=50)
     ap.add_argument("--precision", choices=["exact", "fast"], default="exact")
     ap.add_argument("--schedule", choices=["dataflow", "bricks", "persistent", "per_color"], default="dataflow")
+    ap.add_argument("--grouping", choices=["auto", "elements", "chains", "clusters"], default="auto",
+                    help="xf_grouping: chains = vertex records shared with the thread's next element stay in private shared memory")
     ap.add_argument("--energy", choices=["yeohskinfast", "mixedsel", "mixed", "yeohskin"], default="yeohskinfast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-hint", action="store_true", help="use the generic colouring instead of the lattice 24-colouring")
@@ -119,7 +121,9 @@ def make_scene(xf, args, device, stream):
     geo = xf.GeoLinear3dCuda(nodes, idx, device=device, stream=stream,
                              precision=xf.PRECISION_EXACT if args.precision == "exact" else xf.PRECISION_FAST,
                              schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
-                             color_hint=None if args.no_hint else hint)
+                             color_hint=None if args.no_hint else hint,
+                             grouping={"auto": xf.GROUPING_AUTO, "elements": xf.GROUPING_ELEMENTS, "chains": xf.GROUPING_CHAINS,
+                                       "clusters": xf.GROUPING_CLUSTERS}[args.grouping])
     y_min = float(nodes.reshape(-1, 3)[:, 1].min())
     geo.set_ground(True, y_min - 1.0e-3, 0.0)
     st = xf.make_settings(energy=ENERGY_IDS[args.energy], simultaneous=True, poisson=0.5, compliance=1.0, gravity=(0.0, -0.4905),
@@ -321,22 +325,31 @@ def main():
         ach_hbm = (nT * sub * b_hbm) / (kernel_ms * 1e-3) / 1e9
         ach_l2 = (nT * sub * b_l2) / (kernel_ms * 1e-3) / 1e9
         ws = 56 * nT + 48 * nV
-        traffic = None  # dram__bytes_read+write of ONE launch of the dominant kernel, from the committed ncu capture
+        kernel = {"dataflow": "k_substeps_dataflow", "bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent",
+                  "per_color": "k_sweep_color (x colours)"}[args.schedule]
+        if args.schedule == "dataflow" and info["chainedPermille"] > 0 and info["maxColorSize"] <= info["gridBlocks"] * info["blockThreads"]:
+            kernel = "k_substeps_chain"
+        elif args.schedule == "dataflow" and args.grouping == "clusters":
+            kernel = "k_substeps_cluster"
+        traffic = None  # dram__bytes_read+write of ONE launch of the dominant kernel, from the committed ncu captures
         try:
             with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
                 tj = json.load(f)
-            if (args.cells, args.precision, args.energy, args.schedule) == (55, "exact", "yeohskinfast", tj.get("schedule", "persistent")):
-                traffic = tj["dram_bytes_per_element_substep"] * nT * sub  # per launch of `sub` substeps
+            for cap in tj.get("captures", [tj]):
+                if (args.cells, args.precision, args.energy) == (55, "exact", "yeohskinfast") and cap["kernel"].split("<")[0] == kernel:
+                    traffic = cap["dram_bytes_per_element_substep"] * nT * sub  # per launch of `sub` substeps
         except Exception:
             traffic = None
         roofline = {
             "bound": "hbm", "achieved": ach_hbm, "peak": peak, "unit": "GB/s", "frac": ach_hbm / peak, "traffic": traffic,
             "traffic_source": "profiles/r1_traffic.json (ncu --set full, same kernel and workload)" if traffic else None,
             "algorithmic_bytes_per_launch": nT * sub * b_hbm,
-            "peak_source": peak_src, "kernel": {"dataflow": "k_substeps_dataflow", "bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent", "per_color": "k_sweep_color (x colours)"}[args.schedule],
+            "peak_source": peak_src, "kernel": kernel,
             "bytes_per_element_substep": b_hbm, "units_per_launch": per_launch_units, "kernel_ms": kernel_ms,
             "achieved_l2_gbs": ach_l2, "bytes_per_element_substep_l2": b_l2, "working_set_bytes": ws, "l2_bytes": info["l2Bytes"],
-            "headline_rule": "L2 figure iff working set <= l2/2 (SURVEY 8d); here %s" % ("L2" if ws <= info["l2Bytes"] / 2 else "HBM"),
+            "headline_rule": "SURVEY 8d names the L2 figure when the working set is <= l2/2 (here: %s); `achieved`/`frac` always use "
+                             "the conservative HBM figure against the measured HBM peak, the L2 figure is reported beside it"
+                             % ("yes" if ws <= info["l2Bytes"] / 2 else "no"),
         }
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -344,6 +357,7 @@ def main():
             "dtype": "f32 math / f64 state (%s)" % args.precision, "data": "synthetic",
             "config": {"workload": workload_name(args), "tets": nT, "verts": nV, "colors": info["colorCount"],
                        "substeps_per_step": sub, "precision": args.precision, "schedule": args.schedule,
+                       "grouping": args.grouping, "chained_permille": info["chainedPermille"],
                        "grid": [info["gridBlocks"], info["blockThreads"]], "l2": "flushed between timed steps (512 MiB memset)",
                        "sharding": "one independent scene per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},

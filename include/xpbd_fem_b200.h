@@ -131,7 +131,13 @@ typedef enum xf_schedule {
 typedef enum xf_grouping {
 	XF_GROUPING_AUTO = 0,     /* = XF_GROUPING_ELEMENTS (clusters measured slower at 1M tets, faster at 2M) */
 	XF_GROUPING_ELEMENTS = 1, /* colour single elements (colorHint honoured) */
-	XF_GROUPING_CLUSTERS = 2  /* clusters, whatever the schedule (falls back to elements if that needs > 254 colours) */
+	XF_GROUPING_CLUSTERS = 2, /* clusters, whatever the schedule (falls back to elements if that needs > 254 colours) */
+	/* Elements coloured singly (as XF_GROUPING_ELEMENTS: same colouring, same serial order, same bits), but on the
+	 * barrier-free schedule the thread that ran position j of one colour keeps, in private shared-memory slots, the
+	 * vertex records that position j of the next colour uses again when nobody writes them in between: those corners
+	 * cost no L2 gather / scatter.  With xf_generate_tet_block's ring-ordered hint a cell's six tets move 18 records
+	 * through L2 instead of 48.  Applies when every colour fits one wave of the co-resident grid (else: ELEMENTS). */
+	XF_GROUPING_CHAINS = 3
 } xf_grouping;
 
 typedef struct xf_create_params {
@@ -176,6 +182,10 @@ int xf_get_colors(const xf_scene* scene, uint32_t* colorOfElement);
 /* Barrier-free schedule (XF_SCHEDULE_DATAFLOW): for the k-th element of xf_get_order, the stage code of the previous writer of
  * each of its corners (0 = the substep's vertex phase, else 1 + colour); per vertex the code of its last writer (0 = none). */
 int xf_get_stage_codes(const xf_scene* scene, uint8_t* predCode4, uint8_t* lastCode);
+/* XF_GROUPING_CHAINS: for the k-th element of xf_get_order one word, per corner n bits [5n, 5n+5) = private slot (0-3) |
+ * 8 if the record is gathered from L2 (waiting for its stage tag) | 16 if it is scattered to L2 after the solve; all zero when
+ * the scene is not chained.  outPermille = corner uses served from a slot, per 1000.  Either pointer may be NULL. */
+int xf_get_chain_info(const xf_scene* scene, uint32_t* info, uint32_t* outPermille);
 int xf_get_elements(const xf_scene* scene, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea);
 
 /* ---- stepping (Geo3d::Substep, Geo.cpp:305-356), n substeps with tickId advancing per substep ---- */
@@ -211,6 +221,8 @@ typedef struct xf_info {
 	uint32_t schedule;           /* resolved xf_schedule */
 	uint64_t kernelLaunches;     /* kernels launched by this scene so far */
 	uint64_t l2Bytes;            /* cudaDeviceProp::l2CacheSize */
+	uint32_t chainedPermille;    /* XF_GROUPING_CHAINS: corner uses served from the thread's private slots, per 1000 (else 0) */
+	uint32_t reserved0;
 } xf_info;
 int xf_get_info(const xf_scene* scene, xf_info* out);
 

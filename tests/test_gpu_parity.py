@@ -79,6 +79,55 @@ def test_exact_clustered_coloring_bit_identical(energy, sim, nu, pattern, schedu
     assert geo.CalculateVolume() == orc.volume()
 
 
+@pytest.mark.parametrize("energy,sim,nu,pattern,dims", [
+    (7, True, 0.5, 0, (7, 4)), (4, True, 0.5, 0, (6, 3)), (4, False, 0.4999, 0, (7, 4)), (5, True, 0.495, 1, (6, 4)),
+    (3, False, 0.5, 0, (5, 5)), (5, False, 0.45, 0, (8, 2)), (7, False, 0.5, 1, (4, 4)), (3, True, 0.4999, 0, (12, 1))])
+def test_exact_chained_sweep_bit_identical(energy, sim, nu, pattern, dims):
+    """XF_GROUPING_CHAINS on the barrier-free schedule (k_substeps_chain): the records an element shares with the thread's
+    next element stay in private shared-memory slots.  Same colouring and serial order as XF_GROUPING_ELEMENTS, same bits;
+    several calls (the slots are empty at every call boundary), ground plane, handles and the manipulator on top."""
+    geo, orc = make_pair(dims[0], dims[1], 0.25, pattern=pattern, schedule=xf.SCHEDULE_DATAFLOW, grouping=xf.GROUPING_CHAINS)
+    assert geo.info()["chainedPermille"] >= 500
+    st, ost = settings_pair(energy=energy, simultaneous=sim, poisson=nu)
+    y0 = float(orc.get_state()[0][:, 1].min()) - 2e-5
+    idxs = np.array([1, geo.nV - 2], dtype=np.uint32)
+    tg = np.array([[0.0, 0.08, 0.0], [0.04, 0.05, 0.03]], dtype=np.float32)
+    for s in (geo, orc):
+        s.set_ground(True, y0, 0.1)
+        s.set_handles(idxs, tg)
+    mg, mo = xf.Manipulator(), ob.Manipulator()
+    for m in (mg, mo):
+        m.pos[:] = (0.0, 0.0, 0.3)
+        m.manipPlaneNormal[:] = (0.0, 0.0, 1.0)
+        m.pick0[:] = (0.01, 0.0, 0.0)
+        m.pickDirTarget[:] = (0.02, 0.05, -1.0)
+        m.picked = 1
+        m.pickedPointIdx = geo.nV // 3
+    for n in (1, 2, 40):
+        geo.Substep(st, DT, n, manip=mg)
+        orc.substep(ost, DT, n, manip=mo)
+        assert_bit_exact(geo, orc)
+    assert geo.CalculateVolume() == orc.volume()
+
+
+def test_chained_sweep_matches_plain_dataflow_at_100k_tets():
+    """Many warps per SM, several CTAs per colour: the chained and the plain barrier-free kernels must agree bit for bit
+    (they share the colouring), and the chained one must have run (info)."""
+    nodes, idx, hint = xf.GenerateTetBlock(26, 26, wonkiness=0.15)
+    st = xf.make_settings(energy=xf.Energy_YeohSkinFast, poisson=0.5)
+    out = []
+    for grouping in (xf.GROUPING_CHAINS, xf.GROUPING_ELEMENTS):
+        geo = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_DATAFLOW, color_hint=hint, grouping=grouping)
+        assert (geo.info()["chainedPermille"] == 625) == (grouping == xf.GROUPING_CHAINS)
+        geo.Substep(st, DT, 30)
+        geo.Substep(st, DT, 7)
+        out.append(geo.get_state())
+        geo.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
+    assert np.isfinite(out[0][0]).all()
+
+
 @pytest.mark.parametrize("schedule", SCHEDULES)
 def test_exact_against_unmodified_reference(schedule):
     if not ob.have_ref():

@@ -164,6 +164,84 @@ def test_stage_codes_replay(kind):
     assert np.array_equal(tag, last)
 
 
+@pytest.mark.parametrize("kind", ["lattice_hint", "lattice_generic", "mirrored", "armadillo"])
+def test_chain_info_replay(kind):
+    """XF_GROUPING_CHAINS: emulate k_substeps_chain on the CPU.  One thread per position, four private slots each, L2 records
+    with a stage tag; values are symbolic (a hash of everything that was combined into them).  Every gathered record must carry
+    the tag the element expects, every slot read must find the record of the right vertex, and after the last colour the L2
+    records must equal those of the plain serial order, all of them tagged by their last writer.  Colouring and serial order
+    must be those of XF_GROUPING_ELEMENTS."""
+    kw = {}
+    if kind == "armadillo":
+        if not ob.have_ref():
+            pytest.skip("needs the reference's embedded Armadillo tables")
+        nodes, idx = ob.RefScene.armadillo().get_mesh()
+        kw = dict(density=2.0, auto_resize=True)
+    else:
+        nodes, idx, hint = xf.GenerateTetBlock(7, 4, pattern=1 if kind == "mirrored" else 0, wonkiness=0.1)
+        if kind == "lattice_hint":
+            kw = dict(color_hint=hint)
+    g = host_scene(nodes, idx, grouping=xf.GROUPING_CHAINS, **kw)
+    plain = host_scene(nodes, idx, grouping=xf.GROUPING_ELEMENTS, **kw)
+    order, colors = g.get_order(), g.get_colors()
+    assert np.array_equal(order, plain.get_order()) and np.array_equal(colors, plain.get_colors())
+    assert plain.chain_info()[1] == 0 and not plain.chain_info()[0].any()
+    info, permille = g.chain_info()
+    assert g.info()["chainedPermille"] == permille
+    tets = idx.reshape(-1, 5)[:, 1:].astype(np.int64)
+    pred, last = g.stage_codes()
+    sizes = np.bincount(colors, minlength=g.nColors)
+    start = np.concatenate([[0], np.cumsum(sizes)])
+    if kind == "lattice_hint":
+        assert permille == 625                                  # 30 of a cell's 48 corner uses never leave the thread
+        gathers = sum(bin(int(w) & 0x42108).count("1") for w in info)
+        scatters = sum(bin(int(w) & 0x84210).count("1") for w in info)
+        assert gathers == scatters == 9 * len(tets) // 6
+    if permille == 0:                                           # nothing lines up: the scene runs on the plain kernel
+        assert not info.any()
+        return
+
+    def combine(e, vals):
+        return [hash((int(e), n) + tuple(vals)) for n in range(4)]
+
+    ref = [hash(("rest", v)) for v in range(g.nV)]
+    l2 = list(ref)
+    tag = np.zeros(g.nV, dtype=np.int64)
+    slots = {}                                                  # (position, slot) -> (vertex, value)
+    for substep in range(2):
+        for k, e in enumerate(order):                           # the serial order
+            new = combine(e, [ref[v] for v in tets[e]])
+            for n, v in enumerate(tets[e]):
+                ref[v] = new[n]
+        for c in range(g.nColors):
+            for j in reversed(range(sizes[c])):                 # any order inside a colour
+                k = start[c] + j
+                e, word = order[k], int(info[k])
+                vals = []
+                for n, v in enumerate(tets[e]):
+                    bits = (word >> (5 * n)) & 31
+                    assert bits & 7 < 4
+                    if bits & 8:
+                        assert tag[v] == pred[k][n], "element %d would wait forever" % e
+                        vals.append(l2[v])
+                    else:
+                        held_v, held_val = slots.pop((j, bits & 7))
+                        assert held_v == v
+                        vals.append(held_val)
+                new = combine(e, vals)
+                for n, v in enumerate(tets[e]):
+                    bits = (word >> (5 * n)) & 31
+                    if bits & 16:
+                        l2[v], tag[v] = new[n], 1 + c
+                    else:
+                        assert (j, bits & 7) not in slots
+                        slots[(j, bits & 7)] = (v, new[n])
+        assert not slots                                        # nothing is kept across the vertex phase
+        assert l2 == ref
+        assert np.array_equal(tag, last)
+        tag[:] = 0                                              # the vertex phase rewrites every record
+
+
 def test_bad_color_hint_is_rejected():
     nodes, idx, hint = xf.GenerateTetBlock(3, 3)
     bad = hint.copy()

@@ -21,7 +21,7 @@ LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem
 XF_ABI_VERSION = 1
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
 PRECISION_EXACT, PRECISION_FAST = 0, 1
-GROUPING_AUTO, GROUPING_ELEMENTS, GROUPING_CLUSTERS = 0, 1, 2
+GROUPING_AUTO, GROUPING_ELEMENTS, GROUPING_CLUSTERS, GROUPING_CHAINS = 0, 1, 2, 3
 SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT, SCHEDULE_BRICKS, SCHEDULE_DATAFLOW = 0, 1, 2, 3, 4
 
 # flag word (Settings.h:9-75)
@@ -82,6 +82,7 @@ class Info(C.Structure):
         ("vertCount", C.c_uint32), ("elementCount", C.c_uint32), ("colorCount", C.c_uint32), ("minColorSize", C.c_uint32),
         ("maxColorSize", C.c_uint32), ("smCount", C.c_uint32), ("gridBlocks", C.c_uint32), ("blockThreads", C.c_uint32),
         ("elementRecordBytes", C.c_uint32), ("schedule", C.c_uint32), ("kernelLaunches", C.c_uint64), ("l2Bytes", C.c_uint64),
+        ("chainedPermille", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
 
@@ -118,7 +119,7 @@ _lib = None
 
 EXPORTS = [
     "xf_last_error", "xf_device_count", "xf_default_create_params", "xf_generate_tet_block", "xf_create", "xf_destroy",
-    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_elements", "xf_substep",
+    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_chain_info", "xf_get_elements", "xf_substep",
     "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
     "xf_frame_state_init", "xf_frame_update",
@@ -155,6 +156,7 @@ def lib():
     L.xf_get_order.argtypes = [vp, vp]
     L.xf_get_colors.argtypes = [vp, vp]
     L.xf_get_stage_codes.argtypes = [vp, vp, vp]
+    L.xf_get_chain_info.argtypes = [vp, vp, vp]
     L.xf_get_elements.argtypes = [vp] * 7
     L.xf_substep.argtypes = [vp, vp, vp, f32, u32]
     L.xf_sync.argtypes = [vp]
@@ -325,6 +327,14 @@ class GeoLinear3dCuda:
         last = np.empty(self.nV, dtype=np.uint8)
         _check(lib().xf_get_stage_codes(self._h, _vp(pred), _vp(last)))
         return pred, last
+
+    def chain_info(self):
+        """XF_GROUPING_CHAINS: slot / first / last word of every element (xf_get_order positions) and the per-mille of
+        corner uses served from a private slot."""
+        info = np.empty(self.nT, dtype=np.uint32)
+        permille = C.c_uint32(0)
+        _check(lib().xf_get_chain_info(self._h, _vp(info), C.byref(permille)))
+        return info, permille.value
 
     def get_colors(self):
         c = np.empty(self.nT, dtype=np.uint32)

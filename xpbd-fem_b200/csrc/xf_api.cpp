@@ -32,6 +32,9 @@ namespace {
 		if (_e != cudaSuccess) { return FailCuda(_e, #call); }       \
 	} while (0)
 
+// XF_GROUPING_AUTO on the barrier-free schedule: chained sweep or plain one element per thread
+constexpr bool kChainByDefault = false;
+constexpr uint32_t kChainMinPermille = 100;
 constexpr uint32_t kBrickSlotCap = 3000; // private vertices per CTA kept in shared memory (96 KB; 2 CTAs per SM)
 
 template <typename T>
@@ -56,6 +59,9 @@ struct xf_scene {
 	bool dataflowOk = false;  // stage codes fit the vertex-index top byte / the 24-bit record tag
 	uint32_t verBase = 1;     // first stage tag of the next dataflow launch (24-bit, wraps)
 	uint32_t spinSleepNs = 400; // back-off of the vertex-phase spin (XF_DATAFLOW_SLEEP_NS)
+	bool wantChain = false;   // XF_GROUPING_CHAINS (or AUTO resolved to it)
+	std::vector<uint32_t> chainInfo; // ChainInfo words in serial-order positions (empty: not chained)
+	uint32_t chainedPermille = 0;
 	std::vector<uint32_t> intOfExt, extOfInt; // caller's vertex id <-> device vertex id
 	int smCount = 0;
 	size_t l2Bytes = 0;
@@ -165,6 +171,10 @@ int UploadScene(xf_scene* s) {
 			for (uint32_t k = 0; k < m.nT; k++) { ek[k] = m.clusterInfo[bp.deviceOrder[k]]; }
 			XF_CUDA(Upload(&d.eK, ek));
 			d.groupSize = m.groupSize;
+		} else if (!s->chainInfo.empty() && !bricks && bp.deviceOrder == m.order) { // chained sweep: device order == serial order
+			XF_CUDA(Upload(&d.eK, s->chainInfo));
+			d.chained = 1;
+			for (uint32_t c = 0; c < d.nColors; c++) { d.maxColorSize = std::max(d.maxColorSize, m.colorStart[c + 1] - m.colorStart[c]); }
 		}
 	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
@@ -259,6 +269,21 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 	s->precision = params->precision;
 	s->schedule = params->schedule;
 	s->device = params->device;
+	// chained sweep (XF_GROUPING_CHAINS): AUTO follows kChainByDefault unless XF_CHAIN=0/1 says otherwise
+	if (params->grouping > XF_GROUPING_CHAINS) { delete s; return Fail(XF_ERR_INVALID, "bad grouping"); }
+	{
+		const char* env = getenv("XF_CHAIN");
+		const bool autoChain = env ? atoi(env) != 0 : kChainByDefault;
+		s->wantChain = params->grouping == XF_GROUPING_CHAINS || (params->grouping == XF_GROUPING_AUTO && autoChain);
+	}
+	if (s->wantChain && s->mesh.groupSize <= 1 && s->mesh.nT > 0 && s->mesh.nV <= 0x01000000u && s->mesh.colorStart.size() <= 255u) {
+		std::vector<uint8_t> pred, last;
+		StageCodes(s->mesh, s->mesh.order, &pred, &last);
+		const uint64_t held = ChainInfo(s->mesh, s->mesh.order, pred, &s->chainInfo);
+		s->chainedPermille = (uint32_t)(held * 1000u / (4u * (uint64_t)s->mesh.nT));
+		// nothing to keep (e.g. a generic colouring whose positions do not line up): the plain kernel does the same work cheaper
+		if (s->chainedPermille < kChainMinPermille) { s->chainInfo.clear(); s->chainedPermille = 0; }
+	}
 	if (s->device >= 0) {
 		cudaError_t e = cudaSetDevice(s->device);
 		if (e != cudaSuccess) { delete s; return FailCuda(e, "cudaSetDevice"); }
@@ -328,6 +353,16 @@ int xf_get_stage_codes(const xf_scene* s, uint8_t* predCode4, uint8_t* lastCode)
 	return XF_OK;
 }
 
+int xf_get_chain_info(const xf_scene* s, uint32_t* info, uint32_t* outPermille) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	if (outPermille) { *outPermille = s->chainedPermille; }
+	if (info) {
+		if (s->chainInfo.empty()) { memset(info, 0, sizeof(uint32_t) * s->mesh.nT); }
+		else { memcpy(info, s->chainInfo.data(), sizeof(uint32_t) * s->mesh.nT); }
+	}
+	return XF_OK;
+}
+
 int xf_get_elements(const xf_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea) {
 	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
 	const HostMesh& m = s->mesh;
@@ -359,6 +394,8 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 			p.tickId = st->tickId + done;
 			if (s->dev.groupSize > 1) {
 				XF_CUDA(LaunchSubstepsCluster(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
+			} else if (s->dev.chained) {
+				XF_CUDA(LaunchSubstepsChain(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			} else {
 				XF_CUDA(LaunchSubstepsDataflow(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			}
@@ -545,6 +582,7 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 	out->minColorSize = mn;
 	out->maxColorSize = mx;
 	out->smCount = (uint32_t)s->smCount;
+	out->chainedPermille = s->device < 0 || (s->dev.chained && s->schedule == XF_SCHEDULE_DATAFLOW) ? s->chainedPermille : 0;
 	if (s->schedule == XF_SCHEDULE_BRICKS) {
 		out->gridBlocks = s->dev.nBricks;
 		out->blockThreads = 256;

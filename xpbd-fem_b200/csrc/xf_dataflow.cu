@@ -298,6 +298,145 @@ __global__ void __launch_bounds__(256, 2) k_substeps_cluster(const DeviceScene s
 	}
 }
 
+// ------------------------------------------------------------------------------------------------
+// Chained variant (XF_GROUPING_CHAINS, ChainInfo in xf_prepare.cpp).  Same colouring, same stages, same one element per
+// thread per colour as k_substeps_dataflow, and the same dependence chain: what changes is the traffic.  At 1M tets a stage
+// is a burst of 41.6k elements x 8 records x 32 B = 10.6 MB through L2, ~1700 cycles at the ~6300 B/cycle the L2 slices
+// deliver, out of a 4200-cycle stage.  The thread that ran position j of colour c runs position j of colour c+1; with the
+// ring-ordered lattice hint that is the next tet around the same cell diagonal, which shares a face with the previous one.
+// The three shared records (nobody else writes them in between: the previous-writer code says so) stay in the thread's four
+// private shared-memory slots; only the fourth is gathered (and waited for) and only the record that leaves is scattered.
+// Per cell: 9 gathers + 9 scatters instead of 24 + 24.  Slots are [slot][half][thread] 16-byte units: conflict-free
+// LDS/STS.128, never touched by another thread, so no synchronisation.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChainSlots = 4;
+
+__device__ __forceinline__ VertexRegs ChainLoad(const uint4* cache, uint32_t slot) {
+	const uint4 a = cache[(2u * slot) * 256u], b = cache[(2u * slot + 1u) * 256u];
+	VertexRegs v;
+	v.x[0] = __hiloint2double((int)a.y, (int)a.x);
+	v.x[1] = __hiloint2double((int)a.w, (int)a.z);
+	v.x[2] = __hiloint2double((int)b.y, (int)b.x);
+	v.w = __uint_as_float(b.z);
+	v.flags = b.w;
+	return v;
+}
+__device__ __forceinline__ void ChainStore(uint4* cache, uint32_t slot, const VertexRegs& v) {
+	cache[(2u * slot) * 256u] = make_uint4((uint32_t)__double2loint(v.x[0]), (uint32_t)__double2hiint(v.x[0]), (uint32_t)__double2loint(v.x[1]),
+	                                       (uint32_t)__double2hiint(v.x[1]));
+	cache[(2u * slot + 1u) * 256u] = make_uint4((uint32_t)__double2loint(v.x[2]), (uint32_t)__double2hiint(v.x[2]), __float_as_uint(v.w), v.flags);
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__device__ __forceinline__ void ChainElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, uint4* cache,
+                                             unsigned mask, uint32_t stageBase, uint32_t c, uint32_t sleepNs) {
+	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
+	uint32_t vid[4], expectTag[4], slot[4];
+	bool first[4], last[4];
+	VertexRegs v[4];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		vid[n] = raw[n] & 0x00ffffffu;
+		expectTag[n] = (stageBase + (raw[n] >> 24)) << 8;
+		const uint32_t bits = info >> (5 * n);
+		slot[n] = bits & 3u;
+		first[n] = (bits & 8u) != 0;
+		last[n] = (bits & 16u) != 0;
+	}
+	// the gathers go out first; the slot reads and the compliance divisions sit in their shadow
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		if (first[n]) { v[n] = LoadVertex(sc.Xw, vid[n]); }
+	}
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		if (!first[n]) { v[n] = ChainLoad(cache, slot[n]); }
+	}
+	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	for (uint32_t spins = 0;; spins++) {
+		bool ok[4];
+#pragma unroll
+		for (int n = 0; n < 4; n++) { ok[n] = !first[n] || (v[n].flags & kVerMask) == expectTag[n]; }
+		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
+		if (spins > kSpinLimit) { __trap(); }
+		if (sleepNs) { __nanosleep(sleepNs); }
+#pragma unroll
+		for (int n = 0; n < 4; n++) {
+			if (!ok[n]) { v[n] = LoadVertex(sc.Xw, vid[n]); }
+		}
+	}
+	const uint32_t newTag = (stageBase + 1u + c) << 8;
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n].flags = (v[n].flags & 0xffu) | newTag; }
+	ElemRec r = rec;
+	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
+	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(NoStore{}, p, r, v, ec);
+	// records that leave the thread first (somebody is waiting for them), then the ones it keeps
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		if (last[n]) { StoreVertex(sc.Xw, vid[n], v[n]); }
+	}
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		if (!last[n]) { ChainStore(cache, slot[n], v[n]); }
+	}
+}
+
+template <int ENERGY, bool SIMUL, bool EXACT>
+__global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc, const __grid_constant__ SubstepParams p, uint32_t nSubsteps,
+                                                           uint32_t verBase, uint32_t tuning) {
+	extern __shared__ __align__(16) unsigned char chainSmem[];
+	uint4* cache = reinterpret_cast<uint4*>(chainSmem) + threadIdx.x;
+	const uint32_t lane = threadIdx.x & 31u;
+	const uint32_t gsize = gridDim.x * blockDim.x;
+	const uint32_t warpSlot = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u;
+	const uint32_t mine = warpSlot + lane; // this thread's position in every colour (the host made sure no colour is larger than the grid)
+	const uint32_t nC = p.nColors;
+	const uint32_t stride = nC + 1u;
+	const uint32_t sleepNs = tuning & 0x7fffu, elemSleepNs = tuning >> 16;
+	const bool prefetch = (tuning & 0x8000u) == 0;
+	ElemRec rec;
+	uint32_t info = 0;
+	for (uint32_t s = 0; s <= nSubsteps; s++) {
+		const bool closing = s == nSubsteps;
+		const uint32_t stageBase = verBase + s * stride;
+		if (!closing && p.colorStart[0] + mine < p.colorStart[1]) {
+			DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[0] + mine, rec);
+			info = __ldg(sc.eK + p.colorStart[0] + mine);
+		}
+		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
+			const uint32_t i = i0 + lane;
+			const bool has = i < sc.nV;
+			const unsigned mask = __ballot_sync(0xffffffffu, has);
+			if (has) {
+				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
+				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+			}
+		}
+		if (closing) { break; }
+		for (uint32_t c = 0; c < nC; c++) {
+			const uint32_t end = p.colorStart[c + 1];
+			const uint32_t e0 = p.colorStart[c] + warpSlot;
+			if (e0 < end) {
+				const bool has = e0 + lane < end;
+				const unsigned mask = __ballot_sync(0xffffffffu, has);
+				if (has) { ChainElement<ENERGY, SIMUL, EXACT>(sc, p, rec, info, cache, mask, stageBase, c, elemSleepNs); }
+			}
+			if (c + 1 < nC && p.colorStart[c + 1] + mine < p.colorStart[c + 2]) {
+				DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + mine, rec);
+				info = __ldg(sc.eK + p.colorStart[c + 1] + mine);
+			}
+			if (prefetch) {
+				const uint32_t c2 = c + 2 < nC ? c + 2 : c + 2 - nC; // wraps into the next substep
+				if (p.colorStart[c2] + mine < p.colorStart[c2 + 1]) {
+					DataflowPrefetch<ENERGY, EXACT>(sc, p.colorStart[c2] + mine);
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eK + p.colorStart[c2] + mine));
+				}
+			}
+		}
+	}
+}
+
 namespace {
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 struct ClusterRunner {
@@ -346,6 +485,36 @@ struct DataflowRunner {
 	}
 };
 }  // namespace
+
+namespace {
+template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+struct ChainRunner {
+	static cudaError_t Run(const DeviceScene& sc, const SubstepParams& p, uint32_t nSubsteps, int smCount, uint32_t verBase, uint32_t tuning,
+	                       cudaStream_t st, uint64_t* launches) {
+		auto fn = k_substeps_chain<ENERGY, SIMUL, EXACT>;
+		const size_t smem = 32u * kChainSlots * 256u;
+		static int perSm = 0;
+		if (perSm == 0) {
+			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, smem);
+			if (e != cudaSuccess) { return e; }
+			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
+		}
+		// one position per thread and colour: a colour larger than the co-resident grid runs on the plain kernel
+		if ((uint64_t)sc.maxColorSize > (uint64_t)perSm * (uint64_t)smCount * 256u) {
+			return DataflowRunner<ENERGY, SIMUL, EXACT, DAMPED>::Run(sc, p, nSubsteps, smCount, verBase, tuning, st, launches);
+		}
+		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&tuning };
+		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, smem, st);
+		++*launches;
+		return e;
+	}
+};
+}  // namespace
+
+cudaError_t LaunchSubstepsChain(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                uint32_t tuning, cudaStream_t stream, uint64_t* launchCount) {
+	return DispatchConfig<ChainRunner>(p.energy, p.simultaneous != 0, exact, false, sc, p, nSubsteps, smCount, verBase, tuning, stream, launchCount);
+}
 
 cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                    uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount) {

@@ -73,9 +73,12 @@ struct DeviceScene {
 	uint8_t* lastCode = nullptr;
 	// device vertex id -> caller's vertex id (nullptr = identity); used where state crosses the ABI
 	uint32_t* extOfInt = nullptr;
-	// clustered dataflow (k_substeps_cluster): per element the cluster slot / first / last bits of its corners
+	// clustered dataflow (k_substeps_cluster) and chained dataflow (k_substeps_chain): per element the slot / first / last
+	// bits of its corners
 	uint32_t* eK = nullptr;
 	uint32_t groupSize = 0;
+	uint32_t chained = 0;       // eK holds ChainInfo words (groupSize <= 1)
+	uint32_t maxColorSize = 0;  // the chained kernel needs every colour to fit one wave of the co-resident grid
 };
 
 constexpr int kMaxHandles = 64;
@@ -192,6 +195,8 @@ struct PackedElements {
 // previous writer of each corner (0 = the substep's vertex phase, else 1 + colour); last = per vertex (caller's numbering)
 // the code of its last writer.
 void StageCodes(const HostMesh& mesh, const std::vector<uint32_t>& order, std::vector<uint8_t>* pred, std::vector<uint8_t>* last);
+// Slot / first / last bits for the chained sweep (xf_prepare.cpp); `pred` as produced by StageCodes for the same `order`.
+uint64_t ChainInfo(const HostMesh& mesh, const std::vector<uint32_t>& order, const std::vector<uint8_t>& pred, std::vector<uint32_t>* info);
 void PackElements(const HostMesh& mesh, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out);
 int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
                       std::string* err);
@@ -208,6 +213,9 @@ cudaError_t LaunchSubstepsBricks(const DeviceScene& sc, const SubstepParams& p, 
                                  uint64_t* launchCount);
 cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                    uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount);
+// Falls back to LaunchSubstepsDataflow when a colour does not fit one wave of the grid.
+cudaError_t LaunchSubstepsChain(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                   uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
