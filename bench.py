@@ -48,6 +48,8 @@ def parse_args():
                     help="xf_grouping: chains = vertex records shared with the thread's next element stay in private shared memory")
     ap.add_argument("--energy", choices=["yeohskinfast", "mixedsel", "mixed", "yeohskin"], default="yeohskinfast")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--hint-order", choices=["ring", "type"], default="ring",
+                    help="numbering of the 24 lattice colour classes: ring = 6*class + type (xf_generate_tet_block), type = 4*type + class")
     ap.add_argument("--no-hint", action="store_true", help="use the generic colouring instead of the lattice 24-colouring")
     return ap.parse_args()
 
@@ -118,6 +120,8 @@ class ClockSampler:
 
 def make_scene(xf, args, device, stream):
     nodes, idx, hint = xf.GenerateTetBlock(args.cells, args.cells)
+    if args.hint_order == "type":
+        hint = (4 * (hint % 6) + hint // 6).astype(hint.dtype)
     geo = xf.GeoLinear3dCuda(nodes, idx, device=device, stream=stream,
                              precision=xf.PRECISION_EXACT if args.precision == "exact" else xf.PRECISION_FAST,
                              schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
@@ -357,7 +361,7 @@ def main():
             "dtype": "f32 math / f64 state (%s)" % args.precision, "data": "synthetic",
             "config": {"workload": workload_name(args), "tets": nT, "verts": nV, "colors": info["colorCount"],
                        "substeps_per_step": sub, "precision": args.precision, "schedule": args.schedule,
-                       "grouping": args.grouping, "chained_permille": info["chainedPermille"],
+                       "grouping": args.grouping, "chained_permille": info["chainedPermille"], "hint_order": args.hint_order,
                        "grid": [info["gridBlocks"], info["blockThreads"]], "l2": "flushed between timed steps (512 MiB memset)",
                        "sharding": "one independent scene per GPU, no collective"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": state_bytes, "d2h_bytes_per_step": state_bytes},

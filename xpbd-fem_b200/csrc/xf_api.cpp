@@ -174,8 +174,9 @@ int UploadScene(xf_scene* s) {
 		} else if (!s->chainInfo.empty() && !bricks && bp.deviceOrder == m.order) { // chained sweep: device order == serial order
 			XF_CUDA(Upload(&d.eK, s->chainInfo));
 			d.chained = 1;
-			for (uint32_t c = 0; c < d.nColors; c++) { d.maxColorSize = std::max(d.maxColorSize, m.colorStart[c + 1] - m.colorStart[c]); }
 		}
+		for (uint32_t c = 0; c < d.nColors; c++) { d.maxColorSize = std::max(d.maxColorSize, m.colorStart[c + 1] - m.colorStart[c]); }
+		if (const char* env = getenv("XF_DATAFLOW_BLOCK")) { d.dataflowBlock = (uint32_t)atoi(env); }
 	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
 	if (bricks) {
@@ -588,7 +589,7 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 		out->blockThreads = 256;
 	} else if (s->schedule == XF_SCHEDULE_DATAFLOW) {
 		out->gridBlocks = (uint32_t)(2 * s->smCount);
-		out->blockThreads = 256;
+		out->blockThreads = s->dev.groupSize > 1 ? 256u : (uint32_t)DataflowBlockThreads(s->dev, 2 * s->smCount);
 	} else if (!s->shapes.empty()) {
 		out->gridBlocks = (uint32_t)s->shapes.begin()->second.gridBlocks;
 		out->blockThreads = (uint32_t)s->shapes.begin()->second.blockThreads;

@@ -479,7 +479,8 @@ struct DataflowRunner {
 		}
 		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&sleepNs };
 		// cooperative launch: not for grid.sync (there is none) but because it guarantees that all CTAs are co-resident
-		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, 0, st);
+		const int grid = perSm * smCount;
+		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)grid), dim3((unsigned)DataflowBlockThreads(sc, grid)), args, 0, st);
 		++*launches;
 		return e;
 	}
@@ -504,7 +505,8 @@ struct ChainRunner {
 			return DataflowRunner<ENERGY, SIMUL, EXACT, DAMPED>::Run(sc, p, nSubsteps, smCount, verBase, tuning, st, launches);
 		}
 		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&tuning };
-		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, smem, st);
+		const int grid = perSm * smCount;
+		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)grid), dim3((unsigned)DataflowBlockThreads(sc, grid)), args, smem, st);
 		++*launches;
 		return e;
 	}

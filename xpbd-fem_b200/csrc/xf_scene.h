@@ -79,7 +79,23 @@ struct DeviceScene {
 	uint32_t groupSize = 0;
 	uint32_t chained = 0;       // eK holds ChainInfo words (groupSize <= 1)
 	uint32_t maxColorSize = 0;  // the chained kernel needs every colour to fit one wave of the co-resident grid
+	uint32_t dataflowBlock = 0; // threads per CTA of the barrier-free kernels (0 = DataflowBlockThreads picks)
 };
+
+// Threads per CTA of the barrier-free kernels.  Work is dealt one element per thread and colour, so only
+// ceil(maxColorSize / 32) warps of the grid ever run an element; the others only take part in the vertex phase and poll for
+// it the rest of the time (L2 traffic and issue slots next to the warps on the dependence chain).  Measured on B200
+// (tools/ab_check.sh, profiles/r1_results.md): with no spare warps 384k tets run 9.7 % faster (64 instead of 256 threads:
+// 500 of 2368 warps had work), 24k tets 0.7 % faster; at 1M tets (1300 of 2368 warps busy) 160 threads are 0.8 % SLOWER than
+// 256 - the spare warps shorten the vertex phase by one round.  So: no spare warps while less than half of a 256-thread
+// grid would have work, else 256.  The grid keeps its CTA count (co-resident, one wave per colour when it fits).
+inline int DataflowBlockThreads(const DeviceScene& sc, int gridBlocks) {
+	if (sc.dataflowBlock >= 32 && sc.dataflowBlock <= 256) { return (int)(sc.dataflowBlock & ~31u); }
+	if (gridBlocks <= 0) { return 256; }
+	const uint64_t perCta = ((uint64_t)sc.maxColorSize + (uint64_t)gridBlocks - 1) / (uint64_t)gridBlocks;
+	const uint64_t threads = ((perCta + 31) / 32) * 32;
+	return (int)(threads < 64 ? 64 : (threads > 128 ? 256 : threads));
+}
 
 constexpr int kMaxHandles = 64;
 constexpr int kMaxColors = 256;
