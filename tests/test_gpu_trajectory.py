@@ -143,3 +143,46 @@ def test_full_size_single_substep_against_oracle(big):
     Xo, Vo, wo = orc.get_state()
     assert np.array_equal(Xg, Xo) and np.array_equal(Vg, Vo) and np.array_equal(wg, wo)
     assert geo.CalculateVolume() == orc.volume()
+
+
+@pytest.mark.parametrize("grouping", [xf.GROUPING_AUTO, xf.GROUPING_CHAINS])
+def test_full_size_contact_scene_against_oracle(big, grouping):
+    """BASELINE config 5 at 998 250 tets: a free block (no locks) under full gravity pressed onto the ground plane with
+    friction, eight drag handles and the manipulator pulling on it (extensions x1/x2, mirrored by the oracle).  After 40
+    substeps on the barrier-free schedule the state is handed to the CPU oracle (teacher forcing) and two more substeps must
+    agree bit for bit; nothing may end up below the plane."""
+    nodes, idx, hint = big
+    kw = dict(energy=xf.Energy_MixedSel, poisson=0.5, lock_left=False, gravity=(0.0, -9.81))
+    st, ost = xf.make_settings(**kw), ob.make_settings(**kw)
+    geo = xf.GeoLinear3dCuda(nodes, idx, color_hint=hint, schedule=xf.SCHEDULE_DATAFLOW, grouping=grouping)
+    orc = ob.OracleScene(nodes, idx)
+    orc.set_order(geo.get_order())
+    y0 = float(np.float32(nodes.reshape(-1, 3)[:, 1].min() + 1e-4))   # the plane cuts the bottom layer: contact from the first substep
+    rng = np.random.RandomState(5)
+    handles = rng.choice(geo.nV, 8, replace=False).astype(np.uint32)
+    targets = (nodes.reshape(-1, 3)[handles] + rng.uniform(-0.02, 0.02, (8, 3))).astype(np.float32)
+    mg, mo = xf.Manipulator(), ob.Manipulator()
+    for m in (mg, mo):
+        m.pos[:] = (0.0, 0.0, 0.3)
+        m.manipPlaneNormal[:] = (0.0, 0.0, 1.0)
+        m.pick0[:] = (0.01, 0.0, 0.0)
+        m.pickDirTarget[:] = (0.02, 0.05, -1.0)
+        m.picked = 1
+        m.pickedPointIdx = geo.nV // 2
+    for s in (geo, orc):
+        s.set_ground(True, y0, 0.3)
+        s.set_handles(handles, targets)
+    geo.Substep(st, DT, 1, manip=mg)
+    assert (geo.get_state()[0][:, 1] == y0).sum() >= 56 * 56 - 9   # the whole bottom layer is projected onto the plane
+    geo.Substep(st, DT, 39, manip=mg)
+    X, V, w = geo.get_state()
+    assert np.isfinite(X).all() and np.isfinite(V).all()
+    assert X[:, 1].min() >= y0
+    orc.set_state(X, V, w)
+    geo.Substep(st, DT, 2, manip=mg)
+    orc.substep(ost, DT, 2, manip=mo)
+    Xg, Vg, wg = geo.get_state()
+    Xo, Vo, wo = orc.get_state()
+    assert np.array_equal(Xg, Xo) and np.array_equal(Vg, Vo) and np.array_equal(wg, wo)
+    assert geo.CalculateVolume() == orc.volume()
+    geo.close()

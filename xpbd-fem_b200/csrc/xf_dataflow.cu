@@ -130,6 +130,9 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 	// packed tuning word: bits 0-15 vertex-phase back-off (ns), bits 16-31 element back-off (ns)
 	const uint32_t sleepNs = tuning & 0x7fffu, elemSleepNs = tuning >> 16;
 	const bool prefetch = (tuning & 0x8000u) == 0;
+	// a warp whose first chunk lies beyond the largest colour never runs an element: it only shares the vertex phase, and must
+	// not spend issue slots walking the colours next to the warps that are on the dependence chain
+	const bool spare = warpSlot >= sc.maxColorSize;
 	ElemRec rec;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps; // closing post phase (locks, manipulator, velocities) of the last substep
@@ -146,6 +149,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 			}
 		}
 		if (closing) { break; }
+		if (spare) { continue; }
 		for (uint32_t c = 0; c < nC; c++) {
 			const uint32_t end = p.colorStart[c + 1];
 			uint32_t e0 = p.colorStart[c] + warpSlot;
@@ -395,6 +399,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 	const uint32_t stride = nC + 1u;
 	const uint32_t sleepNs = tuning & 0x7fffu, elemSleepNs = tuning >> 16;
 	const bool prefetch = (tuning & 0x8000u) == 0;
+	const bool spare = warpSlot >= sc.maxColorSize; // never runs an element: vertex phase only
 	ElemRec rec;
 	uint32_t info = 0;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
@@ -414,6 +419,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 			}
 		}
 		if (closing) { break; }
+		if (spare) { continue; }
 		for (uint32_t c = 0; c < nC; c++) {
 			const uint32_t end = p.colorStart[c + 1];
 			const uint32_t e0 = p.colorStart[c] + warpSlot;
