@@ -109,6 +109,16 @@ def test_lattice_hint_gives_24_balanced_colors():
     check_coloring(idx, g.get_colors(), g.get_order(), 24)
     info = g.info()
     assert info["minColorSize"] == info["maxColorSize"] == 8 * 8 * 8 * 6 // 24
+    # ring order: colours 6k .. 6k+5 are the six tets of the cells of class k, index j of each = the same cell, and consecutive
+    # tets share a face that contains the cell diagonal (what the barrier-free kernel's timing and the chained sweep rely on)
+    tets = idx.reshape(-1, 5)[:, 1:]
+    order = g.get_order().reshape(24, -1)
+    assert np.array_equal(hint, 6 * (hint // 6) + np.arange(len(hint)) % 6)
+    for c in range(24):
+        assert np.array_equal(order[c] // 6, order[6 * (c // 6)] // 6) and np.all(order[c] % 6 == c % 6)
+        if c % 6:
+            shared = [len(set(a) & set(b)) for a, b in zip(tets[order[c - 1]], tets[order[c]])]
+            assert set(shared) == {3}
 
 
 @pytest.mark.parametrize("dims,pattern,wonk", [((8, 8), 0, 0.0), ((5, 3), 0, 0.2), ((6, 4), 1, 0.1)])
