@@ -18,7 +18,7 @@ from __graft_entry__ import ROOT, build, load_package
 
 build()
 xf = load_package()
-WORKER = os.path.join(ROOT, "tools", "part_worker.py")
+WORKER = os.path.join(ROOT, "tests", "part_worker.py")
 
 
 def run_ranks(world, args, port, timeout=600):

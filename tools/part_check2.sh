@@ -1,7 +1,7 @@
 #!/bin/bash
 # Two GPUs (gpurun --gpus 2): partitioned-mesh GPU test, parity + timing of one mesh on 2 GPUs, 2-rank bench line.
 mkdir -p gpurun_out
-T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29701 tools/part_worker.py --mode gpu"
+T="timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29701 tests/part_worker.py --mode gpu"
 {
   echo "== tests: partition (2 GPUs)"; timeout 300 python -m pytest tests/test_partition.py -q -m gpu 2>&1 | tail -3
   echo "== 384k parity+timing dataflow"; $T --dims 40 40 --substeps 8 --schedule dataflow --time-substeps 200 2>&1 | grep -E "PART_RESULT|Error" | head -3

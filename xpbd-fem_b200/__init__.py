@@ -227,6 +227,17 @@ def device_count():
     return n.value if rc == 0 else 0
 
 
+def shard_scenes(n_scenes, world, rank):
+    """Scenes [first, first + count) of a batch of `n_scenes` independent scenes that rank `rank` of `world` steps (BASELINE
+    config 3: batches shard over GPUs with no communication).  Contiguous, ragged by at most one scene, every scene owned once;
+    a scene's settings are derived from its GLOBAL index, so the result does not depend on the world size."""
+    if world < 1 or not 0 <= rank < world or n_scenes < 0:
+        raise ValueError("need world >= 1, 0 <= rank < world, n_scenes >= 0")
+    base, extra = divmod(n_scenes, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
+
+
 def block_scale(dim=3.0):
     """(0.7f * kSpacing) * dim in fp32, as Demo::UpdateSettings scales its blocks (Demo.cpp:16, 318)."""
     k_spacing = np.float32(np.float32(20.0) / np.float32(100.0)) / np.float32(31.0)
