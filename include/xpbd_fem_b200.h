@@ -37,7 +37,8 @@
 extern "C" {
 #endif
 
-#define XF_ABI_VERSION 1
+/* 2: xf_info grew (chainedPermille), XF_GROUPING_CHAINS, xf_get_chain_info */
+#define XF_ABI_VERSION 2
 
 typedef enum xf_status {
 	XF_OK = 0,

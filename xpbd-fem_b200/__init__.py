@@ -18,7 +18,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem_b200.so")  # override: kernel-variant experiments only
 
-XF_ABI_VERSION = 1
+XF_ABI_VERSION = 2
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
 PRECISION_EXACT, PRECISION_FAST = 0, 1
 GROUPING_AUTO, GROUPING_ELEMENTS, GROUPING_CLUSTERS, GROUPING_CHAINS = 0, 1, 2, 3
