@@ -304,6 +304,22 @@ int xf_part_sync(xf_partition* part);
 int xf_part_get_state(xf_partition* part, double* X, double* V, float* w); /* local vertices */
 int xf_part_get_info(const xf_partition* part, uint64_t* launches, uint64_t* epoch);
 
+/* ---- measurement / test hooks (no counterpart in the reference; used by bench.py, tools/ and tests/) ----
+ * xf_debug_l2_bandwidth: streaming copy (mode 0: read + write bytes per second) or read (mode 1) over buffers of `bytes`
+ *   each that stay resident in L2, 256-bit accesses, best of `reps` launches of `passes` passes: the L2 peak the roofline
+ *   of an L2-resident mesh is quoted against.
+ * xf_debug_torn_records: stress of the hardware property the barrier-free schedules rely on - a 32-byte-aligned 256-bit
+ *   access is one transaction.  Writer CTAs rewrite records whose four 8-byte words encode one counter, reader CTAs count
+ *   records with mixed words.  remoteDevice >= 0: the writers run on `device` and store over NVLink into `remoteDevice`'s
+ *   memory while `remoteDevice` reads locally (the partitioned schedule's pattern).
+ * xf_debug_scene_knob: 0 = first stage tag of the next barrier-free launch (tag wrap-around test), 1 = polls before a
+ *   waiting warp gives up, 2 = corrupt the last-writer code of device vertex 0 (stall-report test).
+ * xf_debug_barrier_us: cost of a bare grid barrier (several implementations). */
+int xf_debug_l2_bandwidth(int device, int mode, uint64_t bytes, uint32_t passes, int reps, int blocksPerSm, double* outGBs);
+int xf_debug_torn_records(int device, int remoteDevice, uint32_t nRecords, uint32_t rounds, uint64_t* outReads, uint64_t* outTorn);
+int xf_debug_scene_knob(xf_scene* scene, int knob, uint32_t value);
+int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int threads, uint32_t iterations, float* outUsPerBarrier);
+
 #ifdef __cplusplus
 }
 #endif

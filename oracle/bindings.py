@@ -137,6 +137,7 @@ def _load_ref(kind):
     lib.ref_transform.argtypes = [vp, vp]
     lib.ref_volume.restype = f32
     lib.ref_volume.argtypes = [vp]
+    lib.ref_pick.argtypes = [vp, vp, vp, vp, vp]
     lib.ref_substep.argtypes = [vp, vp, vp, f32, u32]
     lib.ref_substep_ext.argtypes = [vp, vp, vp, f32, u32]
     lib.ref_set_ground.argtypes = [vp, C.c_int, f32, f32]
@@ -149,6 +150,15 @@ def _load_ref(kind):
 
 def _vp(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _pick(fn, handle, ray_origin, ray_dir):
+    o = np.ascontiguousarray(ray_origin, dtype=np.float32).reshape(3)
+    d = np.ascontiguousarray(ray_dir, dtype=np.float32).reshape(3)
+    out5 = np.zeros(5, dtype=np.float32)
+    idx = np.zeros(1, dtype=np.uint32)
+    fn(handle, _vp(o), _vp(d), _vp(out5), _vp(idx))
+    return bool(out5[4] != 0.0), int(idx[0]), out5[:3].copy(), float(out5[3])
 
 
 class RefScene:
@@ -249,6 +259,10 @@ class RefScene:
 
     def volume(self):
         return float(self.lib.ref_volume(self.h))
+
+    def pick(self, ray_origin, ray_dir):
+        """Geo3d::Pick -> (found, vertex index, point xyz, distance)."""
+        return _pick(self.lib.ref_pick, self.h, ray_origin, ray_dir)
 
     def substep(self, settings, dt, n=1, manip=None, ext=False):
         f = self.lib.ref_substep_ext if ext else self.lib.ref_substep
@@ -507,6 +521,7 @@ class AdapterScene:
         lib.ref_adapter_volume.argtypes = [vp]
         lib.ref_adapter_transform.argtypes = [vp, vp]
         lib.ref_adapter_get_state.argtypes = [vp, vp, vp, vp]
+        lib.ref_adapter_pick.argtypes = [vp, vp, vp, vp, vp]
         self.lib = lib
         nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
         idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
@@ -539,6 +554,10 @@ class AdapterScene:
 
     def volume(self):
         return float(self.lib.ref_adapter_volume(self.h))
+
+    def pick(self, ray_origin, ray_dir):
+        """Geo::Pick through the virtual interface -> (found, vertex index, point xyz, distance)."""
+        return _pick(self.lib.ref_adapter_pick, self.h, ray_origin, ray_dir)
 
     def transform(self, m9):
         m9 = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)

@@ -214,6 +214,20 @@ void ref_transform(void* h, const float* m9) {
 
 float ref_volume(void* h) { return ((RefScene*)h)->geo->CalculateVolume(); }
 
+// Geo::Pick through the virtual interface (Geo.h:24, Geo.cpp:366-385).  out5 = {point.xyz, distance, found}; idx = the vertex.
+// The reference writes its outputs only when a candidate wins, so they are pre-set to sentinels here.
+static void PickThrough(Geo* geo, const float* rayOrigin3, const float* rayDir3, float* out5, uint32_t* outIdx) {
+	vec3 point(-1.0f, -1.0f, -1.0f);
+	uint32_t idx = 0xffffffffu;
+	float dist = -1.0f;
+	geo->Pick(V3(rayOrigin3), V3(rayDir3), &point, &idx, &dist);
+	out5[0] = point.x; out5[1] = point.y; out5[2] = point.z; out5[3] = dist; out5[4] = idx != 0xffffffffu ? 1.0f : 0.0f;
+	*outIdx = idx;
+}
+void ref_pick(void* h, const float* rayOrigin3, const float* rayDir3, float* out5, uint32_t* outIdx) {
+	PickThrough(((RefScene*)h)->geo, rayOrigin3, rayDir3, out5, outIdx);
+}
+
 // n calls of the reference's own Geo3d::Substep.  `settings160` is the reference's Settings
 // POD verbatim (160 bytes, Settings.h:79-102); tickId is advanced per substep the way
 // Sim::Update does (Demo.cpp:81, 89).
@@ -348,6 +362,9 @@ void ref_adapter_substep(void* h, const void* settings160, const void* manipPod,
 	}
 }
 float ref_adapter_volume(void* h) { return ((AdapterScene*)h)->geo->CalculateVolume(); }
+void ref_adapter_pick(void* h, const float* rayOrigin3, const float* rayDir3, float* out5, uint32_t* outIdx) {
+	PickThrough(((AdapterScene*)h)->geo, rayOrigin3, rayDir3, out5, outIdx);
+}
 void ref_adapter_transform(void* h, const float* m9) { ((AdapterScene*)h)->geo->Transform(mat3(V3(m9 + 0), V3(m9 + 3), V3(m9 + 6))); }
 void ref_adapter_get_state(void* h, double* X, double* V, float* w) {
 	AdapterScene* a = (AdapterScene*)h;

@@ -40,3 +40,35 @@ def test_adapter_matches_reference_geo_through_virtual_interface():
     Xr, Vr, wr = ref_geo.get_state()
     assert np.array_equal(Xc, Xr) and np.array_equal(Vc, Vr) and np.array_equal(wc, wr)
     assert cuda_geo.volume() == ref_geo.volume()
+
+
+def test_adapter_pick_selects_the_reference_vertex():
+    """Geo::Pick (Geo.cpp:366-385) through both implementations: same vertex, point and distance for rays that hit the body, graze
+    it, start inside it, point away from it (nothing in front: outputs untouched), and after the left lock has zeroed the inverse
+    masses of the locked vertices (they must not be grabbed)."""
+    nodes, idx, hint = xf.GenerateTetBlock(6, 4, wonkiness=0.1)
+    cuda_geo = ob.AdapterScene(nodes, idx, color_hint=hint)
+    ref_geo = ob.RefScene.mesh(nodes, idx)
+    ref_geo.set_order(cuda_geo.get_order())
+    st = ob.make_settings(energy=ob.Energy_MixedSel, poisson=0.45, lock_left=True)
+    rng = np.random.default_rng(5)
+    P = nodes.reshape(-1, 3)
+    lo, hi = P.min(axis=0), P.max(axis=0)
+    rays = []
+    for _ in range(40):
+        target = lo + (hi - lo) * rng.random(3)
+        origin = target + np.array([0.0, 0.0, 0.4]) + 0.05 * rng.standard_normal(3)
+        d = target - origin
+        rays.append((origin, d / np.linalg.norm(d)))
+    rays.append((0.5 * (lo + hi), np.array([0.0, 0.0, -1.0])))                       # starts inside
+    rays.append((hi + 0.3, np.array([1.0, 0.0, 0.0])))                               # everything behind the origin
+    rays.append((np.array([lo[0], lo[1], 0.5]), np.array([0.0, 0.0, -1.0])))         # aims at a locked corner
+    for phase in range(2):
+        for origin, d in rays:
+            a = cuda_geo.pick(origin, d)
+            r = ref_geo.pick(origin, d)
+            assert a[0] == r[0] and a[1] == r[1], (phase, origin, d, a, r)
+            assert np.array_equal(a[2], r[2]) and a[3] == r[3]
+        # two substeps: the first zeroes w of the locked vertices (Geo.cpp:320), changing which vertices can be picked
+        cuda_geo.substep(st, DT, 2)
+        ref_geo.substep(st, DT, 2)

@@ -131,6 +131,7 @@ EXPORTS = [
     "xf_part_get_local_elements", "xf_part_get_peers", "xf_part_get_halo", "xf_part_get_order", "xf_part_get_global_color_start",
     "xf_part_get_initial", "xf_part_get_dataflow_codes", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
     "xf_part_get_state", "xf_part_get_info",
+    "xf_debug_l2_bandwidth", "xf_debug_torn_records", "xf_debug_scene_knob", "xf_debug_barrier_us",
 ]
 
 
@@ -208,6 +209,10 @@ def lib():
     L.xf_part_sync.argtypes = [vp]
     L.xf_part_get_state.argtypes = [vp, vp, vp, vp]
     L.xf_part_get_info.argtypes = [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.xf_debug_l2_bandwidth.argtypes = [i32, i32, C.c_uint64, u32, i32, i32, C.POINTER(C.c_double)]
+    L.xf_debug_torn_records.argtypes = [i32, i32, u32, u32, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    L.xf_debug_scene_knob.argtypes = [vp, i32, u32]
+    L.xf_debug_barrier_us.argtypes = [i32, i32, i32, i32, u32, C.POINTER(f32)]
     _lib = L
     return L
 
@@ -225,6 +230,20 @@ def device_count():
     n = C.c_int(0)
     rc = lib().xf_device_count(C.byref(n))
     return n.value if rc == 0 else 0
+
+
+def l2_bandwidth(device=0, mode=0, mbytes=16, passes=200, reps=5, blocks_per_sm=8):
+    """GB/s of an L2-resident streaming copy (mode 0, read + write bytes) or read (mode 1); see xf_debug_l2_bandwidth."""
+    out = C.c_double(0.0)
+    _check(lib().xf_debug_l2_bandwidth(device, mode, int(mbytes) << 20, passes, reps, blocks_per_sm, C.byref(out)))
+    return out.value
+
+
+def torn_records(device=0, remote_device=-1, n_records=1 << 16, rounds=2000):
+    """(reads, torn) of the 256-bit record stress test; see xf_debug_torn_records."""
+    reads, torn = C.c_uint64(0), C.c_uint64(0)
+    _check(lib().xf_debug_torn_records(device, remote_device, n_records, rounds, C.byref(reads), C.byref(torn)))
+    return reads.value, torn.value
 
 
 def shard_scenes(n_scenes, world, rank):
@@ -398,6 +417,9 @@ class GeoLinear3dCuda:
         out = np.zeros(6, dtype=np.float64)
         _check(lib().xf_stats(self._h, C.byref(settings), _vp(out)))
         return dict(volume=out[0], kinetic=out[1], gravitational=out[2], deviatoric=out[3], volumetric=out[4], nonfinite=out[5])
+
+    def debug_knob(self, knob, value):
+        _check(lib().xf_debug_scene_knob(self._h, knob, value))
 
     def info(self):
         i = Info()

@@ -77,6 +77,7 @@ struct xf_scene {
 	double* dPackV = nullptr;
 	float* dPackW = nullptr;
 	std::vector<float> hostScratch;
+	volatile unsigned int* stallWord = nullptr; // pinned host word a barrier-free kernel sets when it gives up on a record
 };
 
 namespace {
@@ -88,6 +89,7 @@ void FreeDevice(xf_scene* s) {
 	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
+	if (s->stallWord) { cudaFreeHost((void*)s->stallWord); }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
 }
 
@@ -193,6 +195,14 @@ int UploadScene(xf_scene* s) {
 	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
 	XF_CUDA(cudaMalloc((void**)&d.barrier, sizeof(unsigned int) * 32));
 	XF_CUDA(cudaMemset(d.barrier, 0, sizeof(unsigned int) * 32));
+	d.errDev = d.barrier + 16;
+	{
+		void* host = nullptr;
+		XF_CUDA(cudaHostAlloc(&host, sizeof(unsigned int), cudaHostAllocMapped));
+		s->stallWord = (volatile unsigned int*)host;
+		*s->stallWord = 0u;
+		XF_CUDA(cudaHostGetDevicePointer((void**)&d.errHost, host, 0));
+	}
 	XF_CUDA(cudaMalloc((void**)&s->dPackX, sizeof(double) * 3 * m.nV));
 	XF_CUDA(cudaMalloc((void**)&s->dPackV, sizeof(double) * 3 * m.nV));
 	XF_CUDA(cudaMalloc((void**)&s->dPackW, sizeof(float) * m.nV));
@@ -204,6 +214,16 @@ int NeedDevice(const xf_scene* s) {
 	if (s->device < 0) { return Fail(XF_ERR_CUDA, "scene was created host-only (device < 0): there is no CPU compute path"); }
 	cudaError_t e = cudaSetDevice(s->device);
 	if (e != cudaSuccess) { return FailCuda(e, "cudaSetDevice"); }
+	return XF_OK;
+}
+
+// After a stream sync: did a barrier-free launch give up on a record (SpinGiveUp)?  The state is then undefined; the scene keeps
+// failing until xf_set_state installs a new one.  The CUDA context is intact, other scenes are unaffected.
+int CheckStall(const xf_scene* s) {
+	if (s->stallWord && *s->stallWord != 0u) {
+		return Fail(XF_ERR_CUDA, "barrier-free schedule stalled: a vertex record never reached its expected stage (state rewritten under a running "
+		                         "launch, or a broken schedule); the state is undefined until xf_set_state");
+	}
 	return XF_OK;
 }
 
@@ -423,7 +443,7 @@ int xf_sync(xf_scene* s) {
 	int rc = NeedDevice(s);
 	if (rc != XF_OK) { return rc; }
 	XF_CUDA(cudaStreamSynchronize(s->stream));
-	return XF_OK;
+	return CheckStall(s);
 }
 
 int xf_set_ground(xf_scene* s, int enabled, float y0, float friction) {
@@ -486,7 +506,7 @@ int xf_get_state(xf_scene* s, double* X, double* V, float* w) {
 	if (V) { XF_CUDA(cudaMemcpyAsync(V, s->dPackV, bytes, cudaMemcpyDeviceToHost, s->stream)); }
 	if (w) { XF_CUDA(cudaMemcpyAsync(w, s->dPackW, sizeof(float) * s->mesh.nV, cudaMemcpyDeviceToHost, s->stream)); }
 	XF_CUDA(cudaStreamSynchronize(s->stream));
-	return XF_OK;
+	return CheckStall(s);
 }
 
 int xf_set_state(xf_scene* s, const double* X, const double* V, const float* w) {
@@ -498,6 +518,10 @@ int xf_set_state(xf_scene* s, const double* X, const double* V, const float* w) 
 	if (w) { XF_CUDA(cudaMemcpyAsync(s->dPackW, w, sizeof(float) * s->mesh.nV, cudaMemcpyHostToDevice, s->stream)); }
 	XF_CUDA(LaunchUnpackState(s->dev, X ? s->dPackX : nullptr, V ? s->dPackV : nullptr, w ? s->dPackW : nullptr, s->stream, &s->launches));
 	XF_CUDA(cudaStreamSynchronize(s->stream));
+	if (s->stallWord && *s->stallWord != 0u) { // a new state ends a reported stall
+		XF_CUDA(cudaMemset(s->dev.errDev, 0, sizeof(unsigned int)));
+		*s->stallWord = 0u;
+	}
 	return XF_OK;
 }
 
@@ -548,6 +572,8 @@ int xf_volume(xf_scene* s, float* outVolume) {
 	s->hostScratch.resize(s->mesh.nT);
 	XF_CUDA(cudaMemcpyAsync(s->hostScratch.data(), s->dev.eScratch, sizeof(float) * s->mesh.nT, cudaMemcpyDeviceToHost, s->stream));
 	XF_CUDA(cudaStreamSynchronize(s->stream));
+	rc = CheckStall(s);
+	if (rc != XF_OK) { return rc; }
 	float volume = 0.0f; // fp32 running sum in element order, Geo.cpp:828-829
 	for (uint32_t e = 0; e < s->mesh.nT; e++) { volume += s->hostScratch[e]; }
 	*outVolume = volume;
@@ -564,7 +590,28 @@ int xf_stats(xf_scene* s, const xf_settings* st, double* out6) {
 	XF_CUDA(LaunchStats(s->dev, p, (double)st->gravity[0], (double)st->gravity[1], s->smCount, s->stream, &s->launches));
 	XF_CUDA(cudaMemcpyAsync(out6, s->dev.statScratch, sizeof(double) * 6, cudaMemcpyDeviceToHost, s->stream));
 	XF_CUDA(cudaStreamSynchronize(s->stream));
-	return XF_OK;
+	return CheckStall(s);
+}
+
+/* Test / measurement hook (declared in the header's debug section).  knob 0: first stage tag of the next barrier-free launch
+ * (24 bits; lets a test cross the tag wrap-around without ~13 000 launches); 1: polls before a waiting warp gives up;
+ * 2: overwrite the last-writer code of device vertex 0 (breaks the schedule on purpose: the next launch must report a stall,
+ * not hang and not kill the context). */
+int xf_debug_scene_knob(xf_scene* s, int knob, uint32_t value) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	switch (knob) {
+	case 0: s->verBase = value & 0x00ffffffu; return XF_OK;
+	case 1: s->dev.spinLimit = value; return XF_OK;
+	case 2: {
+		if (!s->dev.lastCode) { return Fail(XF_ERR_UNSUPPORTED, "scene has no dataflow codes"); }
+		const uint8_t code = (uint8_t)value;
+		XF_CUDA(cudaStreamSynchronize(s->stream));
+		XF_CUDA(cudaMemcpy(s->dev.lastCode, &code, 1, cudaMemcpyHostToDevice));
+		return XF_OK;
+	}
+	default: return Fail(XF_ERR_INVALID, "unknown knob");
+	}
 }
 
 int xf_get_info(const xf_scene* s, xf_info* out) {

@@ -379,7 +379,8 @@ int xf_batch_set_ground(xf_batch* b, int enabled, float y0, float friction) {
 }
 
 // settings: `settingsCount` == 1 (shared by all scenes) or == scene count (one per scene).  Energy, solve mode and
-// Rayleigh type select the kernel instantiation and must be the same for every scene.
+// Rayleigh type select the kernel instantiation and must be the same for every scene; so must volumePasses and the set of
+// damping sweeps that run (they fix the number of group barriers per substep).
 int xf_batch_substep(xf_batch* b, const xf_settings* settings, uint32_t settingsCount, float dt, uint32_t n) {
 	if (!b || !settings) { return Fail(XF_ERR_INVALID, "null argument"); }
 	if (settingsCount != 1 && settingsCount != b->dev.nScenes) { return Fail(XF_ERR_INVALID, "settingsCount must be 1 or the scene count"); }
@@ -398,6 +399,13 @@ int xf_batch_substep(xf_batch* b, const xf_settings* settings, uint32_t settings
 		if (s == 0) { p0 = p; damped0 = damped; }
 		else if (p.energy != p0.energy || p.simultaneous != p0.simultaneous || p.rayleigh != p0.rayleigh || damped != damped0) {
 			return Fail(XF_ERR_UNSUPPORTED, "all scenes of a batch must share energy, solve mode and damping type (scene " + std::to_string(s) + " differs)");
+		}
+		// The kernel's barrier trip counts come from these three: scene groups that share a CTA (or a warp, for tiny meshes) must
+		// execute the same number of group barriers, so they have to agree across the batch (the values of damping, pbdDamping,
+		// compliance, gravity, tickId ... may differ per scene).
+		else if (p.volumePasses != p0.volumePasses || p.doDamp != p0.doDamp || p.doPbdDamp != p0.doPbdDamp) {
+			return Fail(XF_ERR_UNSUPPORTED, "all scenes of a batch must share volumePasses and which damping sweeps run (damping > 0 with a post "
+			                                "Rayleigh type, pbdDamping > 0): scene " + std::to_string(s) + " differs");
 		}
 		SceneConsts& c = b->hConsts[s];
 		c.dt = p.dt; c.dt2 = p.dt2; c.invDt = p.invDt; c.gdtX = p.gdtX; c.gdtY = p.gdtY; c.keep = p.keep;

@@ -35,23 +35,24 @@ namespace {
 
 constexpr uint32_t kVerMask = 0xffffff00u;
 // A record that never reaches the expected stage means a broken schedule (or a caller that rewrote the state while a
-// launch was in flight): fail loudly (launch error) instead of hanging the device.  2^24 polls is seconds, a healthy
-// wait is a few polls.
-constexpr uint32_t kSpinLimit = 1u << 24;
+// launch was in flight): report it (DeviceScene::errDev / errHost -> XF_ERR_CUDA from xf_sync and the getters) and drain the
+// kernel instead of hanging the device or trapping (a trap would poison the CUDA context of every scene of the process).
+// DeviceScene::spinLimit = 2^24 polls is seconds, a healthy wait is a few polls.  A thread that gave up is `dead`: it walks
+// the rest of its loops without touching anything.
 
 // Waiting is warp-uniform on purpose.  A lane that left a spin loop early would be parked at the loop's reconvergence
 // point, and independent thread scheduling releases parked lanes when the spinning ones yield (that is how it guarantees
 // progress): the warp would then run the ~750-instruction element body once per group of lanes.  Measured: 2x slower at
 // every mesh size.  With a vote over the lanes that have work, the warp leaves the loop as one.
 template <bool EXACT>
-__device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, unsigned mask, bool doPost, bool doPredict,
+__device__ __forceinline__ bool DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, unsigned mask, bool doPost, bool doPredict,
                                                bool wait, uint32_t expectTag, uint32_t newTag, uint32_t sleepNs) {
 	VertexRegs v = LoadVertex(sc.Xw, i);
 	if (wait) {
 		for (uint32_t spins = 0;; spins++) {
 			const bool ok = (v.flags & kVerMask) == expectTag;
 			if (__all_sync(mask, ok)) { break; }
-			if (spins > kSpinLimit) { __trap(); }
+			if (SpinGiveUp(sc.errDev, sc.errHost, mask, spins, sc.spinLimit)) { return false; }
 			if (sleepNs) { __nanosleep(sleepNs); }
 			if (!ok) { v = LoadVertex(sc.Xw, i); }
 		}
@@ -59,12 +60,13 @@ __device__ __forceinline__ void DataflowVertex(const DeviceScene& sc, const Subs
 	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict);
 	v.flags = (v.flags & 0xffu) | newTag;
 	StoreVertex(sc.Xw, i, v);
+	return true;
 }
 
 // One element: spin-gather the four versioned records, solve, scatter with this stage's tag.  `mask` = the lanes of
 // this warp that run an element in this step (all of them call this function together).
 template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, unsigned mask, uint32_t stageBase,
+__device__ __forceinline__ bool DataflowElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, unsigned mask, uint32_t stageBase,
                                                 uint32_t c, uint32_t sleepNs) {
 	const GlobalStore vs = StoreOf(sc);
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
@@ -83,7 +85,7 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 #pragma unroll
 		for (int n = 0; n < 4; n++) { ok[n] = (v[n].flags & kVerMask) == expectTag[n]; }
 		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
-		if (spins > kSpinLimit) { __trap(); }
+		if (SpinGiveUp(sc.errDev, sc.errHost, mask, spins, sc.spinLimit)) { return false; }
 		if (sleepNs) { __nanosleep(sleepNs); }
 		// only the stale records are read again (a poll costs L1TEX wavefronts, the resource the sweep runs on)
 #pragma unroll
@@ -97,6 +99,7 @@ __device__ __forceinline__ void DataflowElement(const DeviceScene& sc, const Sub
 	ElemRec r = rec;
 	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
 	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v, ec);
+	return true;
 }
 
 // The record of the stage after next: pulled into L1 now (the planes are read with ld.global.nc, which allocates in L1),
@@ -134,6 +137,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 	// not spend issue slots walking the colours next to the warps that are on the dependence chain
 	const bool spare = warpSlot >= sc.maxColorSize;
 	ElemRec rec;
+	bool dead = false; // gave up on a stalled record (SpinGiveUp): touch nothing any more, just run out of the loops
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps; // closing post phase (locks, manipulator, velocities) of the last substep
 		const uint32_t stageBase = verBase + s * stride;
@@ -141,11 +145,11 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 		// vertex phase: post of the previous substep + predict, once the vertex's last element of that substep has written
 		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) { // warp-uniform trip count
 			const uint32_t i = i0 + lane;
-			const bool has = i < sc.nV;
+			const bool has = i < sc.nV && !dead;
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
 			}
 		}
 		if (closing) { break; }
@@ -154,17 +158,17 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 			const uint32_t end = p.colorStart[c + 1];
 			uint32_t e0 = p.colorStart[c] + warpSlot;
 			if (e0 < end) {
-				const bool has = e0 + lane < end;
+				const bool has = e0 + lane < end && !dead;
 				const unsigned mask = __ballot_sync(0xffffffffu, has);
-				if (has) { DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, rec, mask, stageBase, c, elemSleepNs); }
+				if (has) { dead = !DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, rec, mask, stageBase, c, elemSleepNs); }
 			}
 			for (e0 += gsize; e0 < end; e0 += gsize) {
-				const bool has = e0 + lane < end;
+				const bool has = e0 + lane < end && !dead;
 				const unsigned mask = __ballot_sync(0xffffffffu, has);
 				if (has) {
 					ElemRec more;
 					DataflowLoad<ENERGY, EXACT>(sc, e0 + lane, more);
-					DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, more, mask, stageBase, c, elemSleepNs);
+					dead = !DataflowElement<ENERGY, SIMUL, EXACT>(sc, p, more, mask, stageBase, c, elemSleepNs);
 				}
 			}
 			if (c + 1 < nC && p.colorStart[c + 1] + warpSlot + lane < p.colorStart[c + 2]) {
@@ -187,17 +191,10 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 // cluster never leave the thread; the chain through L2 has one link per cluster colour (8 on a MeshGen lattice)
 // instead of one per colour (24), and a vertex costs one gather and one scatter per cluster instead of per element.
 // ------------------------------------------------------------------------------------------------
-struct NoStore { // the clustered kernel routes the updated records itself
-	__device__ __forceinline__ void StoreX(uint32_t, const VertexRegs&) const {}
-	__device__ __forceinline__ void LoadO(uint32_t, double*) const {}
-	__device__ __forceinline__ void LoadV(uint32_t, double*) const {}
-	__device__ __forceinline__ void StoreV(uint32_t, const double*) const {}
-};
-
 constexpr int kClusterSlots = 8;
 
 template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void ClusterElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, VertexRec* cache,
+__device__ __forceinline__ bool ClusterElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, VertexRec* cache,
                                                unsigned mask, uint32_t stageBase, uint32_t c) {
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4];
@@ -227,7 +224,7 @@ __device__ __forceinline__ void ClusterElement(const DeviceScene& sc, const Subs
 #pragma unroll
 		for (int n = 0; n < 4; n++) { ok[n] = !first[n] || (v[n].flags & kVerMask) == expectTag[n]; }
 		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
-		if (spins > kSpinLimit) { __trap(); }
+		if (SpinGiveUp(sc.errDev, sc.errHost, mask, spins, sc.spinLimit)) { return false; }
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
 			if (!ok[n]) { v[n] = LoadVertex(sc.Xw, vid[n]); }
@@ -247,6 +244,7 @@ __device__ __forceinline__ void ClusterElement(const DeviceScene& sc, const Subs
 			*slot[n] = VertexRec{ v[n].x[0], v[n].x[1], v[n].x[2], v[n].w, v[n].flags };
 		}
 	}
+	return true;
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT>
@@ -260,16 +258,17 @@ __global__ void __launch_bounds__(256, 2) k_substeps_cluster(const DeviceScene s
 	const uint32_t nC = p.nColors, G = sc.groupSize;
 	const uint32_t stride = nC + 1u;
 	const uint32_t sleepNs = tuning & 0x7fffu;
+	bool dead = false;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps;
 		const uint32_t stageBase = verBase + s * stride;
 		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
 			const uint32_t i = i0 + lane;
-			const bool has = i < sc.nV;
+			const bool has = i < sc.nV && !dead;
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
 			}
 		}
 		if (closing) { break; }
@@ -288,13 +287,13 @@ __global__ void __launch_bounds__(256, 2) k_substeps_cluster(const DeviceScene s
 					const uint32_t c = c0 + t;
 					const uint32_t nt = p.colorStart[c + 1] - p.colorStart[c]; // clusters with more than t elements (sizes descend)
 					if (k0 >= nt) { break; }
-					const bool has = k0 + lane < nt;
+					const bool has = k0 + lane < nt && !dead;
 					const unsigned mask = __ballot_sync(0xffffffffu, has);
 					if (has) {
 						const uint32_t e = p.colorStart[c] + k0 + lane;
 						ElemRec rec;
 						DataflowLoad<ENERGY, EXACT>(sc, e, rec);
-						ClusterElement<ENERGY, SIMUL, EXACT>(sc, p, rec, __ldg(sc.eK + e), cache, mask, stageBase, c);
+						dead = !ClusterElement<ENERGY, SIMUL, EXACT>(sc, p, rec, __ldg(sc.eK + e), cache, mask, stageBase, c);
 					}
 				}
 			}
@@ -332,7 +331,7 @@ __device__ __forceinline__ void ChainStore(uint4* cache, uint32_t slot, const Ve
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void ChainElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, uint4* cache,
+__device__ __forceinline__ bool ChainElement(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec, uint32_t info, uint4* cache,
                                              unsigned mask, uint32_t stageBase, uint32_t c, uint32_t sleepNs) {
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4], slot[4];
@@ -362,7 +361,7 @@ __device__ __forceinline__ void ChainElement(const DeviceScene& sc, const Subste
 #pragma unroll
 		for (int n = 0; n < 4; n++) { ok[n] = !first[n] || (v[n].flags & kVerMask) == expectTag[n]; }
 		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
-		if (spins > kSpinLimit) { __trap(); }
+		if (SpinGiveUp(sc.errDev, sc.errHost, mask, spins, sc.spinLimit)) { return false; }
 		if (sleepNs) { __nanosleep(sleepNs); }
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
@@ -384,6 +383,7 @@ __device__ __forceinline__ void ChainElement(const DeviceScene& sc, const Subste
 	for (int n = 0; n < 4; n++) {
 		if (!last[n]) { ChainStore(cache, slot[n], v[n]); }
 	}
+	return true;
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT>
@@ -402,6 +402,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 	const bool spare = warpSlot >= sc.maxColorSize; // never runs an element: vertex phase only
 	ElemRec rec;
 	uint32_t info = 0;
+	bool dead = false;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps;
 		const uint32_t stageBase = verBase + s * stride;
@@ -411,11 +412,11 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 		}
 		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
 			const uint32_t i = i0 + lane;
-			const bool has = i < sc.nV;
+			const bool has = i < sc.nV && !dead;
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
 			}
 		}
 		if (closing) { break; }
@@ -424,9 +425,9 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 			const uint32_t end = p.colorStart[c + 1];
 			const uint32_t e0 = p.colorStart[c] + warpSlot;
 			if (e0 < end) {
-				const bool has = e0 + lane < end;
+				const bool has = e0 + lane < end && !dead;
 				const unsigned mask = __ballot_sync(0xffffffffu, has);
-				if (has) { ChainElement<ENERGY, SIMUL, EXACT>(sc, p, rec, info, cache, mask, stageBase, c, elemSleepNs); }
+				if (has) { dead = !ChainElement<ENERGY, SIMUL, EXACT>(sc, p, rec, info, cache, mask, stageBase, c, elemSleepNs); }
 			}
 			if (c + 1 < nC && p.colorStart[c + 1] + mine < p.colorStart[c + 2]) {
 				DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c + 1] + mine, rec);
@@ -450,14 +451,10 @@ struct ClusterRunner {
 	                       cudaStream_t st, uint64_t* launches) {
 		auto fn = k_substeps_cluster<ENERGY, SIMUL, EXACT>;
 		const size_t smem = sizeof(VertexRec) * kClusterSlots * 256;
-		static int perSm = 0;
-		if (perSm == 0) {
-			cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-			if (e != cudaSuccess) { return e; }
-			e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, smem);
-			if (e != cudaSuccess) { return e; }
-			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
-		}
+		static OccupancyCache cache; // per instantiation AND per device: the shared-memory opt-in is a per-device attribute
+		int perSm = 0;
+		cudaError_t e0 = cache.Get((const void*)fn, 256, smem, true, &perSm);
+		if (e0 != cudaSuccess) { return e0; }
 		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&tuning };
 		cudaError_t e = cudaLaunchCooperativeKernel((const void*)fn, dim3((unsigned)(perSm * smCount)), dim3(256), args, smem, st);
 		++*launches;
@@ -477,12 +474,10 @@ struct DataflowRunner {
 	static cudaError_t Run(const DeviceScene& sc, const SubstepParams& p, uint32_t nSubsteps, int smCount, uint32_t verBase, uint32_t sleepNs,
 	                       cudaStream_t st, uint64_t* launches) {
 		auto fn = k_substeps_dataflow<ENERGY, SIMUL, EXACT>;
-		static int perSm = 0; // per instantiation; the occupancy of a kernel does not change
-		if (perSm == 0) {
-			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, 0);
-			if (e != cudaSuccess) { return e; }
-			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
-		}
+		static OccupancyCache cache; // per instantiation and per device
+		int perSm = 0;
+		cudaError_t e0 = cache.Get((const void*)fn, 256, 0, false, &perSm);
+		if (e0 != cudaSuccess) { return e0; }
 		void* args[] = { (void*)&sc, (void*)&p, (void*)&nSubsteps, (void*)&verBase, (void*)&sleepNs };
 		// cooperative launch: not for grid.sync (there is none) but because it guarantees that all CTAs are co-resident
 		const int grid = perSm * smCount;
@@ -500,12 +495,10 @@ struct ChainRunner {
 	                       cudaStream_t st, uint64_t* launches) {
 		auto fn = k_substeps_chain<ENERGY, SIMUL, EXACT>;
 		const size_t smem = 32u * kChainSlots * 256u;
-		static int perSm = 0;
-		if (perSm == 0) {
-			cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, fn, 256, smem);
-			if (e != cudaSuccess) { return e; }
-			if (perSm < 1) { return cudaErrorLaunchOutOfResources; }
-		}
+		static OccupancyCache cache;
+		int perSm = 0;
+		cudaError_t e0 = cache.Get((const void*)fn, 256, smem, false, &perSm);
+		if (e0 != cudaSuccess) { return e0; }
 		// one position per thread and colour: a colour larger than the co-resident grid runs on the plain kernel
 		if ((uint64_t)sc.maxColorSize > (uint64_t)perSm * (uint64_t)smCount * 256u) {
 			return DataflowRunner<ENERGY, SIMUL, EXACT, DAMPED>::Run(sc, p, nSubsteps, smCount, verBase, tuning, st, launches);

@@ -90,11 +90,16 @@ struct VertexRegs {
 };
 // 32-byte records move as ONE 256-bit L2 request (LDG.E.256 / STG.E.256, sm_100+) instead of two 128-bit ones:
 // the sweep is bound by L2 request/sector throughput in the bursts that follow each barrier.
+// The accesses are STRONG (relaxed, gpu scope): the barrier-free schedules race on these records by design (the tag inside
+// the record is the synchronisation), and a weak racing access would be undefined in the PTX model.  What the model does NOT
+// promise is single-copy atomicity beyond 8 bytes: that one 32-byte-aligned 256-bit access is one L2 sector transaction is a
+// property of sm_100 hardware.  tools/check_sass.py (run by the Makefile) fails the build if these do not come out as
+// LDG/STG.E.ENL2.256.STRONG.GPU, and tests/test_gpu_hardening.py stresses it (xf_debug_torn_records).
 __device__ __forceinline__ void Load32B(const void* p, double& a, double& b, double& c, double& d) {
-	asm volatile("ld.global.cg.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
+	asm volatile("ld.relaxed.gpu.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p) : "memory");
 }
 __device__ __forceinline__ void Store32B(void* p, double a, double b, double c, double d) {
-	asm volatile("st.global.cg.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+	asm volatile("st.relaxed.gpu.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
 __device__ __forceinline__ VertexRegs LoadVertex(const VertexRec* Xw, uint32_t i) {
 	VertexRegs v;
@@ -114,6 +119,31 @@ __device__ __forceinline__ void LoadD3(const double4* A, uint32_t i, double* out
 	Load32B(A + i, out[0], out[1], out[2], pad);
 }
 __device__ __forceinline__ void StoreD3(double4* A, uint32_t i, const double* v) { Store32B(A + i, v[0], v[1], v[2], 0.0); }
+
+// Give-up test of a tag wait, called by every lane of the waiting group with the same `spins` (the groups leave their spin
+// loops as one, see xf_dataflow.cu).  Every 1024 polls: past the limit, report the stall (device word for the other waiters,
+// pinned host word for the host); in any case stop waiting once somebody has reported one.
+__device__ __forceinline__ bool SpinGiveUp(unsigned int* errDev, unsigned int* errHost, unsigned mask, uint32_t spins, uint32_t limit) {
+	if ((spins & 1023u) != 1023u) { return false; }
+	if (spins > limit) {
+		atomicExch(errDev, 1u);
+		if (errHost) {
+			*reinterpret_cast<volatile unsigned int*>(errHost) = 1u;
+			__threadfence_system();
+		}
+	}
+	unsigned int e;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(errDev) : "memory");
+	return __any_sync(mask, e != 0u) != 0;
+}
+
+// Store policy of the kernels that route the updated records themselves.
+struct NoStore {
+	__device__ __forceinline__ void StoreX(uint32_t, const VertexRegs&) const {}
+	__device__ __forceinline__ void LoadO(uint32_t, double*) const {}
+	__device__ __forceinline__ void LoadV(uint32_t, double*) const {}
+	__device__ __forceinline__ void StoreV(uint32_t, const double*) const {}
+};
 
 // Vertex-store policies: where an element's vertices live.  GlobalStore = the HBM/L2 arrays of a DeviceScene
 // (one mesh per device); SmemStore = one small scene resident in shared memory (batched scenes, xf_batch.cu).

@@ -316,7 +316,7 @@ constexpr uint32_t kPartSpinLimit = 1u << 26; // polls before a rank gives up on
 constexpr uint32_t kTagMask = 0xffffff00u;
 
 template <int ENERGY, bool SIMUL, bool EXACT>
-__device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const SubstepParams& p, const ElemRec& rec, unsigned mask, bool iface,
+__device__ __forceinline__ bool PartDataflowElement(const PartDevice& pd, const SubstepParams& p, const ElemRec& rec, unsigned mask, bool iface,
                                                     uint32_t stageBase, uint32_t c) {
 	const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 	uint32_t vid[4], expectTag[4];
@@ -353,7 +353,7 @@ __device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const 
 			ok[n] = ackOk[n] && (v[n].flags & kTagMask) == expectTag[n];
 		}
 		if (__all_sync(mask, ok[0] && ok[1] && ok[2] && ok[3])) { break; }
-		if (spins > kPartSpinLimit) { atomicExch(pd.errorFlag, 1u); __trap(); }
+		if (SpinGiveUp(pd.errorFlag, nullptr, mask, spins, kPartSpinLimit)) { return false; } // report + drain, never trap
 #pragma unroll
 		for (int n = 0; n < 4; n++) {
 			if ((v[n].flags & kTagMask) != expectTag[n]) { v[n] = vs.LoadX(vid[n]); }
@@ -365,6 +365,7 @@ __device__ __forceinline__ void PartDataflowElement(const PartDevice& pd, const 
 	ElemRec r = rec;
 	r.idx = make_uint4(vid[0], vid[1], vid[2], vid[3]);
 	SolveElementGathered<ENERGY, SIMUL, EXACT, false>(vs, p, r, v, ec);
+	return true;
 }
 
 template <int ENERGY, bool SIMUL, bool EXACT>
@@ -386,12 +387,13 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 	const uint32_t nVertList = ifacePool ? pd.nSharedList : pd.nPrivList;
 	const uint32_t nC = pd.nColors;
 	const uint32_t stride = nC + 1u;
+	bool dead = false; // gave up on a stalled record: touch nothing any more, run out of the loops (the host reports XF_ERR_CUDA)
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps;
 		const uint32_t stageBase = verBase + s * stride;
 		// vertex phase on every local copy
 		for (uint32_t k0 = poolSlot; k0 < nVertList; k0 += poolStride) {
-			const bool has = k0 + lane < nVertList;
+			const bool has = k0 + lane < nVertList && !dead;
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t i = __ldg(vertList + k0 + lane);
@@ -401,10 +403,11 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 					for (uint32_t spins = 0;; spins++) {
 						const bool ok = (v.flags & kTagMask) == expectTag;
 						if (__all_sync(mask, ok)) { break; }
-						if (spins > kPartSpinLimit) { atomicExch(pd.errorFlag, 1u); __trap(); }
+						if (SpinGiveUp(pd.errorFlag, nullptr, mask, spins, kPartSpinLimit)) { dead = true; break; }
 						if (!ok) { v = LoadVertexSys(sc.Xw, i); }
 					}
 				}
+				if (dead) { continue; }
 				VertexPhaseBody<EXACT>(sc, p, i, v, s > 0, !closing);
 				v.flags = (v.flags & 0xffu) | (stageBase << 8);
 				StoreVertexSys(sc.Xw, i, v);
@@ -424,12 +427,12 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 			const uint32_t begin = ifacePool ? __ldg(pd.colorStart + c) : mid, end = ifacePool ? mid : __ldg(pd.colorStart + c + 1);
 			for (uint32_t e0 = begin + poolSlot; e0 < end; e0 += poolStride) {
 				const uint32_t e = e0 + lane;
-				const bool has = e < end;
+				const bool has = e < end && !dead;
 				const unsigned mask = __ballot_sync(0xffffffffu, has);
 				if (has) {
 					ElemRec rec;
 					LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
-					PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, ifacePool, stageBase, c);
+					dead = !PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, ifacePool, stageBase, c);
 				}
 			}
 		}

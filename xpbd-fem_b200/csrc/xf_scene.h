@@ -67,6 +67,13 @@ struct DeviceScene {
 	uint32_t nSharedVerts = 0;
 	uint32_t maxPrivPerBrick = 0;
 	unsigned int* barrier = nullptr; // grid-barrier counter
+	// Stall report of the barrier-free schedules.  A record that never reaches the expected stage (a broken schedule, or a caller
+	// that rewrote the state under a running launch) must not hang the device and must not kill the CUDA context either: the warp
+	// that gives up sets both words, every other waiting warp sees errDev within 1024 polls, all of them stop working and the
+	// kernel drains.  errHost is pinned host memory (device alias here), so the host reads the verdict after a plain stream sync.
+	unsigned int* errDev = nullptr;
+	unsigned int* errHost = nullptr;
+	uint32_t spinLimit = 1u << 24; // polls before a waiting warp gives up: seconds (a healthy wait is a few polls)
 	// dataflow schedule (XF_SCHEDULE_DATAFLOW, xf_dataflow.cu): eA whose vertex indices carry, in their top byte, the stage
 	// code of the previous writer of that vertex (0 = vertex phase, 1 + colour otherwise); per vertex the code of its last writer
 	ElemRecA* eAd = nullptr;

@@ -81,19 +81,29 @@ struct GeoLinear3dCuda : public Geo {
 		xf_get_state(scene, hostX.data(), hostV.data(), hostW.data());
 		mirrorValid = true;
 	}
-	// UI helpers (out of the hot-path scope): nearest pickable vertex to the ray, from the host mirror.
+	// Geo3d::Pick (Geo.cpp:366-385) on the host mirror, same selection rule so that a drag grabs the vertex the reference would:
+	// candidates are pickable vertices that still have mass (w != 0: a locked vertex cannot be grabbed) in front of the ray origin;
+	// they are ranked by t * distance-to-ray (t = distance along the ray), ties go to the LATER vertex, and the outputs are
+	// only written when some candidate wins.
 	void Pick(vec3 rayOrigin, vec3 rayDir, vec3* outNearestPoint, uint32_t* outNearestPointIdx, float* outDistance) final {
 		RefreshMirror();
-		float best = FLT_MAX;
+		float bestRank = FLT_MAX;
 		for (uint32_t i = 0; i < hostFlags.size(); i++) {
-			if (!(hostFlags[i] & Geo::Pickable)) { continue; }
-			vec3 p = vec3((float)hostX[3 * i], (float)hostX[3 * i + 1], (float)hostX[3 * i + 2]);
-			float t = dot(rayDir, p - rayOrigin);
-			if (t < 0.0f) { continue; }
-			float d = distance(p, rayOrigin + t * rayDir);
-			if (d < best) { best = d; *outNearestPoint = p; *outNearestPointIdx = i; }
+			if (!(hostFlags[i] & Geo::Pickable) || hostW[i] == 0.0f) { continue; }
+			const vec3 p = vec3(dvec3(hostX[3 * i], hostX[3 * i + 1], hostX[3 * i + 2]));
+			float dist = FLT_MAX, rank = FLT_MAX;
+			const float t = dot(rayDir, p - rayOrigin);
+			if (t >= 0.0f) {
+				dist = distance(p, rayOrigin + t * rayDir);
+				rank = t * dist;
+			}
+			if (bestRank >= rank) {
+				bestRank = rank;
+				*outDistance = dist;
+				*outNearestPoint = p;
+				*outNearestPointIdx = i;
+			}
 		}
-		*outDistance = best;
 	}
 	void Render(const Settings&) final { RefreshMirror(); /* draw from hostX with the host's renderer */ }
 };
