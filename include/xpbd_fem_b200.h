@@ -223,8 +223,18 @@ typedef struct xf_info {
 	uint64_t kernelLaunches;     /* kernels launched by this scene so far */
 	uint64_t l2Bytes;            /* cudaDeviceProp::l2CacheSize */
 	uint32_t chainedPermille;    /* XF_GROUPING_CHAINS: corner uses served from the thread's private slots, per 1000 (else 0) */
-	uint32_t reserved0;
+	uint32_t lastKernel;         /* xf_kernel_id of the stepping kernel the last xf_substep launched (0 = none yet) */
 } xf_info;
+/* which stepping kernel ran (xf_info::lastKernel): lets a caller (and the tests) see when a call left the barrier-free path */
+typedef enum xf_kernel_id {
+	XF_KERNEL_NONE = 0,
+	XF_KERNEL_DATAFLOW = 1,      /* k_substeps_dataflow: barrier-free, versioned records */
+	XF_KERNEL_CHAIN = 2,         /* k_substeps_chain */
+	XF_KERNEL_CLUSTER = 3,       /* k_substeps_cluster */
+	XF_KERNEL_PERSISTENT = 4,    /* k_substeps_persistent: grid barrier per colour */
+	XF_KERNEL_BRICKS = 5,        /* k_substeps_bricks */
+	XF_KERNEL_PER_COLOR = 6      /* k_sweep_color / k_vertex_phase, one launch per colour */
+} xf_kernel_id;
 int xf_get_info(const xf_scene* scene, xf_info* out);
 
 /* ---- frame driver: Sim::Update (Demo.cpp:37-103) for one Geo ----

@@ -82,8 +82,20 @@ class Info(C.Structure):
         ("vertCount", C.c_uint32), ("elementCount", C.c_uint32), ("colorCount", C.c_uint32), ("minColorSize", C.c_uint32),
         ("maxColorSize", C.c_uint32), ("smCount", C.c_uint32), ("gridBlocks", C.c_uint32), ("blockThreads", C.c_uint32),
         ("elementRecordBytes", C.c_uint32), ("schedule", C.c_uint32), ("kernelLaunches", C.c_uint64), ("l2Bytes", C.c_uint64),
-        ("chainedPermille", C.c_uint32), ("reserved0", C.c_uint32),
+        ("chainedPermille", C.c_uint32), ("lastKernelId", C.c_uint32),
     ]
+
+
+KERNEL_NAMES = {0: None, 1: "k_substeps_dataflow", 2: "k_substeps_chain", 3: "k_substeps_cluster", 4: "k_substeps_persistent",
+                5: "k_substeps_bricks", 6: "k_sweep_color (x colours)"}
+
+
+def frame_constants(settings, state):
+    """Sim::Update's per-frame derived constants (time-corrected drag / PBD damping, Demo.cpp:51-63) written into `settings`,
+    without stepping anything (xf_frame_update with a NULL scene and dt = 0)."""
+    n = C.c_uint32(0)
+    _check(lib().xf_frame_update(None, C.byref(settings), None, 0.0, 1.0 / 60.0, C.byref(state), C.byref(n)))
+    return settings
 
 
 def new_frame_state():
@@ -424,7 +436,9 @@ class GeoLinear3dCuda:
     def info(self):
         i = Info()
         _check(lib().xf_get_info(self._h, C.byref(i)))
-        return {k: getattr(i, k) for k, _ in Info._fields_}
+        d = {k: getattr(i, k) for k, _ in Info._fields_}
+        d["lastKernel"] = KERNEL_NAMES.get(d["lastKernelId"])
+        return d
 
     def get_state_async(self, X_ptr, V_ptr):
         """Enqueue device->host copies into caller-owned (pinned) buffers; pointers are integers or None."""

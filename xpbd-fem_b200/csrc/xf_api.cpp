@@ -66,6 +66,7 @@ struct xf_scene {
 	int smCount = 0;
 	size_t l2Bytes = 0;
 	uint64_t launches = 0;
+	uint32_t lastKernel = 0;  // xf_kernel_id of the last stepping launch
 	// extensions
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
@@ -413,6 +414,7 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 		for (uint32_t done = 0; done < n;) {
 			const uint32_t m = std::min(n - done, maxPerLaunch);
 			p.tickId = st->tickId + done;
+			s->lastKernel = s->dev.groupSize > 1 ? XF_KERNEL_CLUSTER : (s->dev.chained ? XF_KERNEL_CHAIN : XF_KERNEL_DATAFLOW);
 			if (s->dev.groupSize > 1) {
 				XF_CUDA(LaunchSubstepsCluster(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			} else if (s->dev.chained) {
@@ -424,6 +426,7 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 			done += m;
 		}
 	} else if (s->schedule == XF_SCHEDULE_BRICKS) {
+		s->lastKernel = XF_KERNEL_BRICKS;
 		XF_CUDA(LaunchSubstepsBricks(s->dev, p, exact, n, s->smCount, s->stream, &s->launches));
 	} else if (s->schedule == XF_SCHEDULE_PERSISTENT || s->schedule == XF_SCHEDULE_DATAFLOW) {
 		auto it = s->shapes.find(p.energy);
@@ -432,8 +435,10 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 			XF_CUDA(QueryLaunchShape(s->device, p.energy, exact, &shape));
 			it = s->shapes.emplace(p.energy, shape).first;
 		}
+		s->lastKernel = XF_KERNEL_PERSISTENT;
 		XF_CUDA(LaunchSubstepsPersistent(s->dev, p, exact, n, it->second, s->stream, &s->launches));
 	} else {
+		s->lastKernel = XF_KERNEL_PER_COLOR;
 		XF_CUDA(LaunchSubstepsPerColor(s->dev, p, exact, n, s->stream, &s->launches));
 	}
 	return XF_OK;
@@ -643,6 +648,7 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 	}
 	out->elementRecordBytes = s->precision == XF_PRECISION_EXACT ? 80u : 64u; // +16 B only for prefactored energies in EXACT
 	out->schedule = (uint32_t)s->schedule;
+	out->lastKernel = s->lastKernel;
 	out->kernelLaunches = s->launches;
 	out->l2Bytes = s->l2Bytes;
 	return XF_OK;
