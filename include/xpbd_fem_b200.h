@@ -233,7 +233,8 @@ typedef enum xf_kernel_id {
 	XF_KERNEL_CLUSTER = 3,       /* k_substeps_cluster */
 	XF_KERNEL_PERSISTENT = 4,    /* k_substeps_persistent: grid barrier per colour */
 	XF_KERNEL_BRICKS = 5,        /* k_substeps_bricks */
-	XF_KERNEL_PER_COLOR = 6      /* k_sweep_color / k_vertex_phase, one launch per colour */
+	XF_KERNEL_PER_COLOR = 6,     /* k_sweep_color / k_vertex_phase, one launch per colour */
+	XF_KERNEL_DATAFLOW_GENERAL = 7 /* k_substeps_dataflow_general: barrier-free with volume passes / post-solve damping sweeps */
 } xf_kernel_id;
 int xf_get_info(const xf_scene* scene, xf_info* out);
 

@@ -48,6 +48,31 @@ def test_stage_tags_wrap_around(grouping):
     geo.close()
 
 
+def test_stage_tags_wrap_around_with_damping_sweeps_and_volume_passes():
+    """The same wrap on k_substeps_dataflow_general (stride = 1 + colours * (1 + volume passes) + 1 tags per substep)."""
+    nodes, idx, hint = xf.GenerateTetBlock(6, 5, wonkiness=0.2)
+    geo = xf.GeoLinear3dCuda(nodes, idx, device=0, schedule=xf.SCHEDULE_DATAFLOW, color_hint=hint)
+    stride = 1 + geo.nColors * 2 + 1
+    geo.debug_knob(0, (1 << 24) - 3 * stride)
+    kw = dict(energy=xf.Energy_YeohSkinFast, poisson=0.495, damping=0.005, rayleigh=3, pbd_damping=0.03, volume_passes=1)
+    st, ost = xf.make_settings(**kw), ob.make_settings(**kw)
+    for s in (st, ost):
+        s.volumeAndTimeCorrectedPbdDamping = 1e-6
+        s.amortizedVolumeAndTimeCorrectedPbdDamping = 7e-6
+    orc = ob.OracleScene(nodes, idx)
+    orc.set_order(geo.get_order())
+    for launch in range(6):
+        geo.Substep(st, DT, 4)
+        orc.substep(ost, DT, 4)
+        st.tickId += 4
+        ost.tickId += 4
+        X, V, w = geo.get_state()
+        Xo, Vo, wo = orc.get_state()
+        assert np.array_equal(X, Xo) and np.array_equal(V, Vo) and np.array_equal(w, wo), "launch %d" % launch
+    assert geo.info()["lastKernel"] == "k_substeps_dataflow_general"
+    geo.close()
+
+
 def test_a_stalled_schedule_is_reported_and_the_context_survives():
     nodes, idx, hint = xf.GenerateTetBlock(6, 5)
     broken = xf.GeoLinear3dCuda(nodes, idx, device=0, schedule=xf.SCHEDULE_DATAFLOW, color_hint=hint)

@@ -158,6 +158,39 @@ def test_exact_damping_variants(rayleigh, sim, energy, schedule):
         st.tickId += n   # Sim::Update advances tickId per substep (Demo.cpp:81, 89)
         ost.tickId += n
         assert_bit_exact(geo, orc)
+    if schedule == xf.SCHEDULE_DATAFLOW:
+        # post-solve damping sweeps stay on the barrier-free schedule; only in-constraint damping (Paper / Limit) needs grid barriers
+        assert geo.info()["lastKernel"] == ("k_substeps_dataflow_general" if rayleigh >= 2 else "k_substeps_persistent")
+
+
+@pytest.mark.parametrize("rayleigh", [2, 3])
+@pytest.mark.parametrize("pbd,volume_passes", [(0.03, 0), (0.0, 0), (0.03, 2)])
+def test_exact_damped_default_scene_barrier_free_24k_tets(rayleigh, pbd, volume_passes):
+    """The web demo's default damping (wasm/ui.js:76-88: Rayleigh_PostAmortized 0.005, pbdDamping 0.03, drag) at 24 576 tets, over more
+    than one amortisation period and across launches, on k_substeps_dataflow_general: V records versioned by write counts."""
+    nodes, idx, hint = xf.GenerateTetBlock(16, 16, wonkiness=0.2)
+    geo = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_DATAFLOW, color_hint=hint)
+    orc = ob.OracleScene(nodes, idx)
+    orc.set_order(geo.get_order())
+    kw = dict(energy=xf.Energy_MixedSel, simultaneous=True, poisson=0.495, damping=0.005, rayleigh=rayleigh, pbd_damping=pbd, drag_tc=0.0007,
+              volume_passes=volume_passes)
+    st, ost = settings_pair(**kw)
+    for s in (st, ost):
+        s.volumeAndTimeCorrectedPbdDamping = 1e-6
+        s.amortizedVolumeAndTimeCorrectedPbdDamping = 7e-6
+    for n in (1, 11, 13):
+        geo.Substep(st, DT, n)
+        orc.substep(ost, DT, n)
+        st.tickId += n
+        ost.tickId += n
+        assert_bit_exact(geo, orc)
+    assert geo.info()["lastKernel"] == "k_substeps_dataflow_general"
+    # and back to the plain kernel in the same scene: the tags of the two kernels do not collide
+    st2, ost2 = settings_pair(energy=xf.Energy_MixedSel, poisson=0.495)
+    geo.Substep(st2, DT, 5)
+    orc.substep(ost2, DT, 5)
+    assert_bit_exact(geo, orc)
+    assert geo.info()["lastKernel"] == "k_substeps_dataflow"
 
 
 @pytest.mark.parametrize("schedule", SCHEDULES)
@@ -179,6 +212,8 @@ def test_exact_volume_passes_lock_right_manipulator(schedule):
     geo.Substep(st, DT, 20, manip=mg)
     orc.substep(ost, DT, 20, manip=mo)
     assert_bit_exact(geo, orc)
+    if schedule == xf.SCHEDULE_DATAFLOW:
+        assert geo.info()["lastKernel"] == "k_substeps_dataflow_general"
 
 
 @pytest.mark.parametrize("schedule", SCHEDULES)

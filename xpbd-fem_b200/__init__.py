@@ -87,7 +87,7 @@ class Info(C.Structure):
 
 
 KERNEL_NAMES = {0: None, 1: "k_substeps_dataflow", 2: "k_substeps_chain", 3: "k_substeps_cluster", 4: "k_substeps_persistent",
-                5: "k_substeps_bricks", 6: "k_sweep_color (x colours)"}
+                5: "k_substeps_bricks", 6: "k_sweep_color (x colours)", 7: "k_substeps_dataflow_general"}
 
 
 def frame_constants(settings, state):

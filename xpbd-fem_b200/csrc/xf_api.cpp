@@ -67,6 +67,7 @@ struct xf_scene {
 	size_t l2Bytes = 0;
 	uint64_t launches = 0;
 	uint32_t lastKernel = 0;  // xf_kernel_id of the last stepping launch
+	uint64_t vEpoch = 1;      // substeps stepped by k_substeps_dataflow_general so far (V-record tags)
 	// extensions
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
@@ -87,7 +88,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->stallWord) { cudaFreeHost((void*)s->stallWord); }
@@ -177,6 +178,28 @@ int UploadScene(xf_scene* s) {
 		} else if (!s->chainInfo.empty() && !bricks && bp.deviceOrder == m.order) { // chained sweep: device order == serial order
 			XF_CUDA(Upload(&d.eK, s->chainInfo));
 			d.chained = 1;
+		}
+		if (!bricks && m.groupSize <= 1 && bp.deviceOrder == m.order) {
+			// damping sweeps on the barrier-free schedule (xf_dataflow_general.cu): V records are versioned by a write count.
+			// Rank of every element among the elements around each of its corners' vertices (serial order), and per vertex how
+			// many of those elements lie below each boundary nT*q/8 of the amortised damping slices (Geo.cpp:794-797).
+			std::vector<uint32_t> rank(m.nT, 0);
+			std::vector<uint8_t> seen(m.nV, 0);
+			std::vector<uint64_t> below(m.nV, 0);
+			uint32_t bound[XF_AMORTIZATION_PERIOD + 1];
+			for (uint32_t q = 0; q <= XF_AMORTIZATION_PERIOD; q++) { bound[q] = (uint32_t)(((uint64_t)m.nT * q) / XF_AMORTIZATION_PERIOD); }
+			for (uint32_t k = 0, q0 = 1; k < m.nT; k++) {
+				while (q0 < XF_AMORTIZATION_PERIOD && k >= bound[q0]) { q0++; } // first boundary above position k
+				for (int j = 0; j < 4; j++) {
+					const uint32_t v = devIdx[4 * (size_t)k + j];
+					rank[k] |= (uint32_t)seen[v]++ << (8 * j);
+					for (uint32_t q = q0; q <= XF_AMORTIZATION_PERIOD; q++) { below[v] += 1ull << (8 * (q - 1)); }
+				}
+			}
+			std::vector<uint2> slice(m.nV);
+			for (uint32_t v = 0; v < m.nV; v++) { slice[v] = make_uint2((uint32_t)below[v], (uint32_t)(below[v] >> 32)); }
+			XF_CUDA(Upload(&d.eRank, rank));
+			XF_CUDA(Upload(&d.vSlice, slice));
 		}
 		for (uint32_t c = 0; c < d.nColors; c++) { d.maxColorSize = std::max(d.maxColorSize, m.colorStart[c + 1] - m.colorStart[c]); }
 		if (const char* env = getenv("XF_DATAFLOW_BLOCK")) { d.dataflowBlock = (uint32_t)atoi(env); }
@@ -406,16 +429,22 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 	rc = BuildParams(s, st, manip, dt, &p);
 	if (rc != XF_OK) { return rc; }
 	const bool exact = s->precision == XF_PRECISION_EXACT;
-	// the barrier-free schedule covers the undamped main sweep; everything else runs with grid barriers
-	const bool plainSweep = !(p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST) && !p.doDamp && !p.doPbdDamp && p.volumePasses == 0;
-	if (s->schedule == XF_SCHEDULE_DATAFLOW && plainSweep) {
-		const uint32_t stride = p.nColors + 1u;
-		const uint32_t maxPerLaunch = (0x00ffffffu - 2u) / stride; // tags of one launch must not wrap onto the stale ones
+	// the barrier-free schedule covers everything but in-constraint Rayleigh damping (Paper / Limit read O of other threads' vertices)
+	const bool inConstraintDamping = p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST;
+	const bool plainSweep = !inConstraintDamping && !p.doDamp && !p.doPbdDamp && p.volumePasses == 0;
+	const bool generalOk = !inConstraintDamping && s->dev.eRank && !s->dev.chained && s->dev.groupSize <= 1 && !getenv("XF_NO_DATAFLOW_GENERAL");
+	if (s->schedule == XF_SCHEDULE_DATAFLOW && (plainSweep || generalOk)) {
+		const uint32_t stride = plainSweep ? p.nColors + 1u : DataflowGeneralStride(p);
+		const uint32_t maxPerLaunch = std::max(1u, (0x00ffffffu - 2u) / stride); // tags of one launch must not wrap onto the stale ones
 		for (uint32_t done = 0; done < n;) {
 			const uint32_t m = std::min(n - done, maxPerLaunch);
 			p.tickId = st->tickId + done;
-			s->lastKernel = s->dev.groupSize > 1 ? XF_KERNEL_CLUSTER : (s->dev.chained ? XF_KERNEL_CHAIN : XF_KERNEL_DATAFLOW);
-			if (s->dev.groupSize > 1) {
+			s->lastKernel = !plainSweep ? XF_KERNEL_DATAFLOW_GENERAL
+			                            : (s->dev.groupSize > 1 ? XF_KERNEL_CLUSTER : (s->dev.chained ? XF_KERNEL_CHAIN : XF_KERNEL_DATAFLOW));
+			if (!plainSweep) {
+				XF_CUDA(LaunchSubstepsDataflowGeneral(s->dev, p, exact, m, s->smCount, s->verBase, s->vEpoch, s->spinSleepNs, s->stream, &s->launches));
+				s->vEpoch += m;
+			} else if (s->dev.groupSize > 1) {
 				XF_CUDA(LaunchSubstepsCluster(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));
 			} else if (s->dev.chained) {
 				XF_CUDA(LaunchSubstepsChain(s->dev, p, exact, m, s->smCount, s->verBase, s->spinSleepNs, s->stream, &s->launches));

@@ -560,17 +560,14 @@ __device__ __forceinline__ void SolveVolumeOnly(const VS& vs, const PARAMS& p, c
 }
 
 // DampElement: SolveElementMixed in DampingMode::On, Fem.cpp:910-929, 555-563; RayleighDamp Xpbd.h:216-263.
-template <int ENERGY, bool SIMUL, bool EXACT, typename VS, typename PARAMS>
-__device__ __forceinline__ void DampElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
+// The arithmetic with the four position records and velocities already in registers (`vel` is updated in place); the
+// barrier-free kernels gather and scatter the versioned records themselves.
+template <int ENERGY, bool SIMUL, bool EXACT, typename PARAMS>
+__device__ __forceinline__ void DampElementGathered(const PARAMS& p, const ElemRec& e, const VertexRegs (&v)[4], double (&vel)[4][3]) {
 	typedef Op<EXACT> O;
-	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
-	VertexRegs v[4];
-	double vel[4][3];
 	float fv[4][3];
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
-		v[n] = vs.LoadX(is[n]);
-		vs.LoadV(is[n], vel[n]);
 #pragma unroll
 		for (int k = 0; k < 3; k++) { fv[n][k] = __double2float_rn(vel[n][k]); }
 	}
@@ -632,6 +629,18 @@ __device__ __forceinline__ void DampElement(const VS& vs, const PARAMS& p, const
 			}
 		}
 	}
+}
+template <int ENERGY, bool SIMUL, bool EXACT, typename VS, typename PARAMS>
+__device__ __forceinline__ void DampElement(const VS& vs, const PARAMS& p, const ElemRec& e) {
+	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
+	VertexRegs v[4];
+	double vel[4][3];
+#pragma unroll
+	for (int n = 0; n < 4; n++) {
+		v[n] = vs.LoadX(is[n]);
+		vs.LoadV(is[n], vel[n]);
+	}
+	DampElementGathered<ENERGY, SIMUL, EXACT>(p, e, v, vel);
 #pragma unroll
 	for (int n = 0; n < 4; n++) { vs.StoreV(is[n], vel[n]); }
 }
@@ -666,15 +675,10 @@ __device__ __forceinline__ void InverseViaDouble(const float (&m)[3][3], float (
 }
 
 // PbdDamp<4>, Xpbd.h:309-348
-template <bool EXACT, typename VS, typename PARAMS>
-__device__ __forceinline__ void PbdDampElement(const VS& vs, const PARAMS& p, float surfaceArea, const uint4& idx) {
+template <bool EXACT, typename PARAMS>
+__device__ __forceinline__ void PbdDampGathered(const PARAMS& p, float surfaceArea, const VertexRegs (&v)[4], double (&vel)[4][3]) {
 	typedef Op<EXACT> O;
-	const uint32_t is[4] = { idx.x, idx.y, idx.z, idx.w };
 	float damping = fminf(1.0f, O::div(p.pbdDamping, surfaceArea));
-	VertexRegs v[4];
-	double vel[4][3];
-#pragma unroll
-	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); vs.LoadV(is[n], vel[n]); }
 	float X[4][3], Vf[4][3], M[4];
 	float Wsum = 1.0e-8f;
 #pragma unroll
@@ -733,8 +737,18 @@ __device__ __forceinline__ void PbdDampElement(const VS& vs, const PARAMS& p, fl
 			float dV = O::sub(O::add(Vcm[k], cr[k]), Vf[n][k]);
 			vel[n][k] = O::dadd(vel[n][k], (double)O::mul(damping, dV));
 		}
-		vs.StoreV(is[n], vel[n]);
 	}
+}
+template <bool EXACT, typename VS, typename PARAMS>
+__device__ __forceinline__ void PbdDampElement(const VS& vs, const PARAMS& p, float surfaceArea, const uint4& idx) {
+	const uint32_t is[4] = { idx.x, idx.y, idx.z, idx.w };
+	VertexRegs v[4];
+	double vel[4][3];
+#pragma unroll
+	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(is[n]); vs.LoadV(is[n], vel[n]); }
+	PbdDampGathered<EXACT>(p, surfaceArea, v, vel);
+#pragma unroll
+	for (int n = 0; n < 4; n++) { vs.StoreV(is[n], vel[n]); }
 }
 
 }  // namespace xf

@@ -24,8 +24,11 @@ __device__ __forceinline__ void DragTowards(VertexRegs& v, const float* target, 
 
 // Body of the vertex phase for vertex `i` (global id) whose position record is already in registers; O, V (and X0
 // for the right lock) are read/written in global memory.  The caller stores `v` back to wherever it lives.
+// `vTag` goes into the spare fourth word of the V record: the barrier-free kernels with damping sweeps version V records
+// the way they version position records (xf_dataflow_general.cu); 0.0 everywhere else.
 template <bool EXACT>
-__device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const SubstepParams& p, uint32_t i, VertexRegs& v, bool doPost, bool doPredict) {
+__device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const SubstepParams& p, uint32_t i, VertexRegs& v, bool doPost, bool doPredict,
+                                                double vTag = 0.0) {
 	typedef Op<EXACT> O;
 	double o[3], vel[3];
 	LoadD3(sc.O, i, o);
@@ -79,7 +82,7 @@ __device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const Sub
 		}
 	}
 	StoreD3(sc.O, i, o);
-	StoreD3(sc.V, i, vel);
+	Store32B(sc.V + i, vel[0], vel[1], vel[2], vTag);
 }
 
 template <bool EXACT>

@@ -87,6 +87,12 @@ struct DeviceScene {
 	uint32_t chained = 0;       // eK holds ChainInfo words (groupSize <= 1)
 	uint32_t maxColorSize = 0;  // the chained kernel needs every colour to fit one wave of the co-resident grid
 	uint32_t dataflowBlock = 0; // threads per CTA of the barrier-free kernels (0 = DataflowBlockThreads picks)
+	// damping sweeps on the barrier-free schedule (k_substeps_dataflow_general): V records are versioned by a write COUNT.
+	// eRank: per element 4 x 8 bits, the rank of the element among the elements around each corner's vertex (serial order);
+	// vSlice: per vertex 8 x 8 bits, the number of elements around it whose serial position is below nT*q/8, q = 1..8
+	// (the amortised damping slices of Geo.cpp:794-797; byte 7 = the valence)
+	uint32_t* eRank = nullptr;
+	uint2* vSlice = nullptr;
 };
 
 // Threads per CTA of the barrier-free kernels.  Work is dealt one element per thread and colour, so only
@@ -239,6 +245,11 @@ cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p
 // Falls back to LaunchSubstepsDataflow when a colour does not fit one wave of the grid.
 cudaError_t LaunchSubstepsChain(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                 uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
+// Volume passes and post-solve damping sweeps (Rayleigh_Post / PostAmortized, PbdDamp) without barriers; `vEpoch` numbers the
+// substeps of the scene's life (V-record tags), `stride` = stages per substep (the caller advances verBase by n * stride + 1).
+uint32_t DataflowGeneralStride(const SubstepParams& p);
+cudaError_t LaunchSubstepsDataflowGeneral(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
+                                          uint64_t vEpoch, uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                   uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
