@@ -501,11 +501,21 @@ __device__ __forceinline__ ElemCompliance ComplianceOf(const PARAMS& p, float vo
 	return c;
 }
 
+}  // namespace xf
+#include "xf_element_packed.cuh" // the same arithmetic two-wide (FMUL2 / FADD2) for the headline configurations
+namespace xf {
+
 // One element of the main sweep with its four vertex records already in registers (`v` is updated and stored).
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS, typename PARAMS>
 __device__ __forceinline__ void SolveElementGathered(const VS& vs, const PARAMS& p, const ElemRec& e, VertexRegs (&v)[4], const ElemCompliance& ec) {
 	typedef Op<EXACT> O;
 	const uint32_t is[4] = { e.idx.x, e.idx.y, e.idx.z, e.idx.w };
+	if (UsePacked<ENERGY, SIMUL, EXACT, DAMPED>::value) {
+		SolvePrefactoredSimulPacked<ENERGY>(p, e, v, ec);
+#pragma unroll
+		for (int n = 0; n < 4; n++) { vs.StoreX(is[n], v[n]); }
+		return;
+	}
 	const float comp0 = ec.comp0, comp1 = ec.comp1;
 	float P[3][3], F[3][3], g0[4][3], g1[4][3];
 	float U0, U1;
