@@ -191,6 +191,13 @@ int xf_get_elements(const xf_scene* scene, uint32_t* idx4, float* Qi9, float* QQ
 
 /* ---- stepping (Geo3d::Substep, Geo.cpp:305-356), n substeps with tickId advancing per substep ---- */
 int xf_substep(xf_scene* scene, const xf_settings* settings, const xf_manipulator* manip, float dt, uint32_t n);
+/* n substeps in ONE launch while Settings::lockedRightTransform3d and / or Manipulator::pickDirTarget change from substep to
+ * substep - what Sim::Update does between its Geo::Substep calls (Demo.cpp:67-90).  lockT3d: n x 12 floats or NULL;
+ * pickDirTarget: n x 3 floats or NULL (used when manip->picked).  tickId advances by one per substep.  Bit-identical to n calls
+ * of xf_substep(.., 1) with those values.  xf_frame_update uses it, so an interactive frame (dragging, animated lock) is one
+ * launch. */
+int xf_substep_varying(xf_scene* scene, const xf_settings* settings, const xf_manipulator* manip, float dt, uint32_t n, const float* lockT3d,
+                       const float* pickDirTarget);
 int xf_sync(xf_scene* scene);
 
 /* Extensions named by the task that the reference lacks (semantics in DESIGN.md §Extensions). */
@@ -252,6 +259,31 @@ typedef struct xf_frame_state {
 void xf_frame_state_init(xf_frame_state* state);
 int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipulator* manip, float dt, float medianFrameTime, xf_frame_state* state,
                     uint32_t* outSubsteps);
+
+/* ---- Sim (Demo.h:18-52): several Geos under one Settings block and one frame clock ----
+ * xf_sim_add_block = Sim::AddBlock (Demo.cpp:120-154; density 2 when autoResize, Demo.cpp:123), xf_sim_add_block_from_settings
+ * = the block Demo::UpdateSettings builds from the shape / pattern / wonkiness in the Settings (table Demo.cpp:289-318,
+ * exposed by xf_block_from_settings), xf_sim_finish_adding_blocks = Sim::FinishAddingBlocks (Demo.cpp:156-168),
+ * xf_sim_set_geo_offset = Sim::SetGeoOffset (Demo.cpp:179-186), xf_sim_update = Sim::Update (Demo.cpp:37-103) with the
+ * manipulator acting on geo `pickedGeo` (Manipulator::pickedGeo; -1 = none), xf_sim_reset = Sim::Reset.  Only Element_T4
+ * blocks; every geo is an xf_scene (xf_sim_geo) on params->device / stream and is stepped with one launch per frame. */
+typedef struct xf_sim xf_sim;
+int xf_sim_create(const xf_create_params* params, xf_sim** outSim);
+int xf_sim_destroy(xf_sim* sim);
+int xf_sim_reset(xf_sim* sim);
+int xf_sim_add_block(xf_sim* sim, uint32_t elementType, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream,
+                     uint32_t idxCount, int autoResize, const uint32_t* colorHint, uint32_t colorHintCount);
+int xf_block_from_settings(const xf_settings* settings, uint32_t* outWidth, uint32_t* outHeight, float* outScaleX, float* outScaleY,
+                           uint32_t* outPattern);
+int xf_sim_add_block_from_settings(xf_sim* sim, const xf_settings* settings);
+int xf_sim_finish_adding_blocks(xf_sim* sim, const xf_settings* settings);
+int xf_sim_set_geo_offset(xf_sim* sim, float x, float y);
+int xf_sim_update(xf_sim* sim, xf_settings* settings, xf_manipulator* manip, int pickedGeo, float dt, float medianFrameTime,
+                  uint32_t* outSubsteps);
+uint32_t xf_sim_geo_count(const xf_sim* sim);
+xf_scene* xf_sim_geo(xf_sim* sim, uint32_t index);
+float xf_sim_volume0(const xf_sim* sim, uint32_t index);
+int xf_sim_get_frame_state(const xf_sim* sim, xf_frame_state* out);
 
 /* ---- batched scenes (BASELINE config 3): nScenes independent instances of ONE rest mesh, each with its own
  * state and Settings, e.g. a vector of RL environments.  The reference would hold them as nScenes Geo objects and

@@ -313,6 +313,7 @@ def _load_oracle():
     lib.xo_get_origin.argtypes = [vp, vp]
     lib.xo_substep.argtypes = [vp, vp, vp, f32, u32]
     lib.xo_set_ground.argtypes = [vp, C.c_int, f32, f32]
+    lib.xo_set_state_precision.argtypes = [vp, C.c_int]
     lib.xo_phase_predict.argtypes = [vp, vp, f32]
     lib.xo_phase_sweep.argtypes = [vp, vp, f32, u32, u32]
     lib.xo_phase_post.argtypes = [vp, vp, vp, f32]
@@ -445,6 +446,10 @@ class OracleScene:
     def set_ground(self, enabled, y0=0.0, friction=0.0):
         self.lib.xo_set_ground(self.h, 1 if enabled else 0, y0, friction)
 
+    def set_state_precision(self, f32):
+        """Study mode: keep X, O, V as fp32 would (tools/fp32_state_study.py); not the reference's algorithm."""
+        self.lib.xo_set_state_precision(self.h, int(f32))  # bit 0: X as fp32, bit 1: V and O too
+
     def set_handles(self, vert_idx, targets):
         vert_idx = np.ascontiguousarray(vert_idx, dtype=np.uint32)
         targets = np.ascontiguousarray(targets, dtype=np.float32).reshape(-1)
@@ -501,6 +506,90 @@ class RefSim:
 
 # ---------------------------------------------------------------------------------------------
 # The product's reference-side adapter (GeoLinear3dCuda : Geo) hosted by the reference harness
+class RefMultiSim:
+    """The reference's Sim holding several T4 blocks (Sim::AddBlock / FinishAddingBlocks / Update), or the block
+    Demo::UpdateSettings builds from a Settings block (from_settings: shape table of Demo.cpp:289-318)."""
+
+    def __init__(self, settings, kind="strict", from_settings=False):
+        lib = _load_ref(kind)
+        vp, u32, f32 = C.c_void_p, C.c_uint32, C.c_float
+        lib.ref_multi_create.restype = vp
+        lib.ref_multi_create.argtypes = [vp]
+        lib.ref_multi_from_settings.restype = vp
+        lib.ref_multi_from_settings.argtypes = [vp]
+        lib.ref_multi_destroy.argtypes = [vp]
+        lib.ref_multi_add_block.argtypes = [vp, vp, u32, vp, u32, C.c_int]
+        lib.ref_multi_finish.argtypes = [vp]
+        lib.ref_multi_set_geo_offset.argtypes = [vp, f32, f32]
+        lib.ref_multi_geo_count.restype = u32
+        lib.ref_multi_geo_count.argtypes = [vp]
+        lib.ref_multi_geo_sizes.argtypes = [vp, u32, vp, vp]
+        lib.ref_multi_volume0.restype = f32
+        lib.ref_multi_volume0.argtypes = [vp, u32]
+        lib.ref_multi_set_order.argtypes = [vp, u32, vp]
+        lib.ref_multi_get_mesh.argtypes = [vp, u32, vp, vp]
+        lib.ref_multi_get_state.argtypes = [vp, u32, vp, vp, vp]
+        lib.ref_multi_update.restype = u32
+        lib.ref_multi_update.argtypes = [vp, vp, vp, C.c_int, f32, f32]
+        self.lib = lib
+        self.h = C.c_void_p(lib.ref_multi_from_settings(C.byref(settings)) if from_settings else lib.ref_multi_create(C.byref(settings)))
+
+    def close(self):
+        if self.h:
+            self.lib.ref_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def add_block(self, nodes, idx_stream, auto_resize=False):
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        self.lib.ref_multi_add_block(self.h, _vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, 1 if auto_resize else 0)
+
+    def finish(self):
+        self.lib.ref_multi_finish(self.h)
+
+    def set_geo_offset(self, x, y):
+        self.lib.ref_multi_set_geo_offset(self.h, x, y)
+
+    def geo_count(self):
+        return int(self.lib.ref_multi_geo_count(self.h))
+
+    def sizes(self, geo):
+        nv, nt = C.c_uint32(), C.c_uint32()
+        self.lib.ref_multi_geo_sizes(self.h, geo, C.byref(nv), C.byref(nt))
+        return nv.value, nt.value
+
+    def volume0(self, geo):
+        return float(self.lib.ref_multi_volume0(self.h, geo))
+
+    def set_order(self, geo, order):
+        order = np.ascontiguousarray(order, dtype=np.uint32)
+        self.lib.ref_multi_set_order(self.h, geo, _vp(order))
+
+    def get_mesh(self, geo):
+        nv, nt = self.sizes(geo)
+        X0 = np.empty((nv, 3), dtype=np.float64)
+        idx = np.empty((nt, 4), dtype=np.uint32)
+        self.lib.ref_multi_get_mesh(self.h, geo, _vp(X0), _vp(idx))
+        return X0, idx
+
+    def get_state(self, geo):
+        nv, _ = self.sizes(geo)
+        X = np.empty((nv, 3), dtype=np.float64)
+        V = np.empty((nv, 3), dtype=np.float64)
+        w = np.empty(nv, dtype=np.float32)
+        self.lib.ref_multi_get_state(self.h, geo, _vp(X), _vp(V), _vp(w))
+        return X, V, w
+
+    def update(self, settings, dt, median_frame_time, manip=None, picked_geo=-1):
+        return self.lib.ref_multi_update(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, picked_geo, dt, median_frame_time)
+
+
 # ---------------------------------------------------------------------------------------------
 class AdapterScene:
     """oracle/_ref/libxpbd_ref_adapter.so: the reference's `Geo` virtual interface, implemented by the CUDA library."""

@@ -421,6 +421,81 @@ uint32_t ref_sim_update(void* h, void* settings160, void* manipPod, float dt, fl
 	return sim->tickId - tick0;
 }
 
+// ---- Sim with several geos, and the block Demo::UpdateSettings builds from a Settings block (shape table, Demo.cpp:289-318) ----
+struct RefMulti {
+	Demo* demo = nullptr; // owns the Sim when the block came from Demo::UpdateSettings
+	Sim* sim = nullptr;
+};
+void* ref_multi_create(const void* settings160) {
+	RefMulti* r = new RefMulti();
+	r->sim = new Sim();
+	r->sim->Reset();
+	memcpy((void*)&r->sim->settings, settings160, sizeof(Settings));
+	return r;
+}
+// Demo::UpdateSettings(0, settings) on a fresh Demo: generates the block the settings describe, AddBlock, FinishAddingBlocks
+void* ref_multi_from_settings(const void* settings160) {
+	RefMulti* r = new RefMulti();
+	r->demo = new Demo();
+	r->demo->sims[0].Reset();
+	r->demo->sims[1].Reset();
+	Settings st;
+	memcpy((void*)&st, settings160, sizeof(Settings));
+	st.flags |= Settings_ConstructBlockFromSettings | Settings_ForceResetBlock;
+	r->demo->UpdateSettings(0, st);
+	r->sim = &r->demo->sims[0];
+	return r;
+}
+void ref_multi_destroy(void* h) {
+	RefMulti* r = (RefMulti*)h;
+	if (!r) { return; }
+	if (r->demo) { delete r->demo; } else { delete r->sim; }
+	delete r;
+}
+void ref_multi_add_block(void* h, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, int autoResize) {
+	((RefMulti*)h)->sim->AddBlock(Element_T4, nodeXYZ, nodeFloatCount, idxStream, idxCount, autoResize != 0);
+}
+void ref_multi_finish(void* h) { ((RefMulti*)h)->sim->FinishAddingBlocks(); }
+void ref_multi_set_geo_offset(void* h, float x, float y) { ((RefMulti*)h)->sim->SetGeoOffset(vec2(x, y)); }
+uint32_t ref_multi_geo_count(void* h) { return ((RefMulti*)h)->sim->geoCount; }
+void ref_multi_geo_sizes(void* h, uint32_t geo, uint32_t* nV, uint32_t* nT) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefMulti*)h)->sim->geos[geo];
+	*nV = g->vertCount;
+	*nT = g->con.tetCount;
+}
+float ref_multi_volume0(void* h, uint32_t geo) { return ((RefMulti*)h)->sim->geos[geo]->volume0; }
+void ref_multi_set_order(void* h, uint32_t geo, const uint32_t* order) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefMulti*)h)->sim->geos[geo];
+	memcpy(g->tOrder, order, sizeof(uint32_t) * g->con.tetCount);
+}
+void ref_multi_get_mesh(void* h, uint32_t geo, double* X0, uint32_t* idx4) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefMulti*)h)->sim->geos[geo];
+	for (uint32_t i = 0; i < g->vertCount; i++) { X0[3 * i + 0] = g->X0[i].x; X0[3 * i + 1] = g->X0[i].y; X0[3 * i + 2] = g->X0[i].z; }
+	for (uint32_t t = 0; t < g->con.tetCount; t++) { for (int j = 0; j < 4; j++) { idx4[4 * t + j] = g->t[t].i[j]; } }
+}
+void ref_multi_get_state(void* h, uint32_t geo, double* X, double* V, float* w) {
+	GeoLinear3d* g = (GeoLinear3d*)((RefMulti*)h)->sim->geos[geo];
+	for (uint32_t i = 0; i < g->vertCount; i++) {
+		if (X) { X[3 * i + 0] = g->X[i].x; X[3 * i + 1] = g->X[i].y; X[3 * i + 2] = g->X[i].z; }
+		if (V) { V[3 * i + 0] = g->V[i].x; V[3 * i + 1] = g->V[i].y; V[3 * i + 2] = g->V[i].z; }
+		if (w) { w[i] = g->w[i]; }
+	}
+}
+// One Sim::Update; the manipulator holds geo `pickedGeo` (-1: nothing)
+uint32_t ref_multi_update(void* h, void* settings160, void* manipPod, int pickedGeo, float dt, float medianFrameTime) {
+	Sim* sim = ((RefMulti*)h)->sim;
+	Settings in;
+	memcpy((void*)&in, settings160, sizeof(Settings));
+	sim->settings = in;
+	ManipPod* mp = (ManipPod*)manipPod;
+	Manipulator manip = ToManip(mp, pickedGeo >= 0 ? sim->geos[pickedGeo] : nullptr);
+	const uint32_t tick0 = sim->tickId;
+	sim->Update(dt, medianFrameTime, &manip);
+	memcpy(settings160, (void*)&sim->settings, sizeof(Settings));
+	if (mp) { mp->pickDirTarget[0] = manip.pickDirTarget.x; mp->pickDirTarget[1] = manip.pickDirTarget.y; mp->pickDirTarget[2] = manip.pickDirTarget.z; }
+	return sim->tickId - tick0;
+}
+
 // Timing leg for bench.py: run `n` reference substeps and return elapsed seconds.
 double ref_time_substeps(void* h, const void* settings160, float dt, uint32_t n) {
 	auto t0 = std::chrono::steady_clock::now();

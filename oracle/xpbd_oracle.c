@@ -50,6 +50,7 @@ struct xo_scene {
 	float origin[3];
 	int groundOn;
 	float groundY, groundFriction;
+	int stateF32; /* study mode (xo_set_state_precision): X, O, V are rounded to fp32 after every write, as a 16-byte record would hold them */
 	uint32_t handleCount;
 	uint32_t handleIdx[64];
 	float handleTarget[64][3];
@@ -721,13 +722,34 @@ static void pbd_damp(const double* Xd, double* Vd, const float* W, const uint32_
 	}
 }
 
+/* Study mode only (not part of the reference's algorithm): what an fp32 {x, y, z} vertex record would keep. */
+void xo_set_state_precision(xo_scene* s, int f32) { s->stateF32 = f32; }
+/* mode bit 0: positions (the record elements share); bit 1: velocities and previous positions too */
+static int rounds(const xo_scene* s, const double* A) { return A == s->X ? (s->stateF32 & 1) : (s->stateF32 & 2); }
+static void round_tet(const xo_scene* s, double* A, const xo_tet* t) {
+	if (!rounds(s, A)) { return; }
+	for (int n = 0; n < 4; n++) {
+		for (int k = 0; k < 3; k++) { size_t q = 3 * (size_t)t->i[n] + k; A[q] = (double)(float)A[q]; }
+	}
+}
+static void round_all(const xo_scene* s, double* A) {
+	if (!rounds(s, A)) { return; }
+	for (size_t q = 0; q < 3 * (size_t)s->nV; q++) { A[q] = (double)(float)A[q]; }
+}
+
 /* GeoLinear3d::Constrain, Geo.cpp:774-788 (tets only) */
 static void constrain(xo_scene* s, const xo_settings* st, float dt) {
 	uint32_t energy = (st->flags >> XO_ENERGY_BIT) & XO_ENERGY_MASK;
 	if (!energy_supported(energy)) { energy = EN_MIXED_SEL; }
-	for (uint32_t i = 0; i < s->nT; i++) { solve_element_mixed(energy, 0, dt, s->X, s->O, NULL, s->w, &s->t[s->tOrder[i]], st); }
+	for (uint32_t i = 0; i < s->nT; i++) {
+		solve_element_mixed(energy, 0, dt, s->X, s->O, NULL, s->w, &s->t[s->tOrder[i]], st);
+		round_tet(s, s->X, &s->t[s->tOrder[i]]);
+	}
 	for (uint32_t itr = 0; itr < st->volumePasses; itr++) {
-		for (uint32_t i = 0; i < s->nT; i++) { solve_volume_only(dt, s->X, s->O, s->w, &s->t[s->tOrder[i]], st); }
+		for (uint32_t i = 0; i < s->nT; i++) {
+			solve_volume_only(dt, s->X, s->O, s->w, &s->t[s->tOrder[i]], st);
+			round_tet(s, s->X, &s->t[s->tOrder[i]]);
+		}
 	}
 }
 
@@ -743,12 +765,14 @@ static void damp(xo_scene* s, const xo_settings* st, float dt) {
 		for (uint32_t i = begin; i < end; i++) {
 			if (st->damping <= 0.0f) { break; } /* TDampElement early-out, Fem.cpp:911 */
 			solve_element_mixed(energy, 1, dt, s->X, NULL, s->V, s->w, &s->t[s->tOrder[i]], st);
+			round_tet(s, s->V, &s->t[s->tOrder[i]]);
 		}
 	}
 	if (st->pbdDamping > 0.0f) {
 		for (uint32_t i = begin; i < end; i++) {
 			const xo_tet* t = &s->t[s->tOrder[i]];
 			pbd_damp(s->X, s->V, s->w, t->i, fminf(1.0f, st->volumeAndTimeCorrectedPbdDamping / t->surfaceArea));
+			round_tet(s, s->V, t);
 		}
 	}
 }
@@ -851,8 +875,10 @@ void xo_substep(xo_scene* s, const xo_settings* settingsIn, const xo_manipulator
 	xo_settings st = *settingsIn;
 	for (uint32_t step = 0; step < n; step++) {
 		xo_phase_predict(s, &st, dt);
+		round_all(s, s->X); round_all(s, s->V); round_all(s, s->O);
 		constrain(s, &st, dt);
 		xo_phase_post(s, &st, manip, dt);
+		round_all(s, s->X); round_all(s, s->V);
 		/* damping, Geo.cpp:346-355 */
 		uint32_t rayleighType = (st.flags >> XO_RAYLEIGH_BIT) & XO_RAYLEIGH_MASK;
 		if (rayleighType == RAY_POST_AMORTIZED) {

@@ -64,6 +64,8 @@ void xo_phase_sweep(xo_scene* s, const xo_settings* settings, float dt, uint32_t
 void xo_phase_post(xo_scene* s, const xo_settings* settings, const xo_manipulator* manip, float dt);
 void xo_set_flags(xo_scene* s, const uint8_t* flags);
 void xo_set_ground(xo_scene* s, int enabled, float y0, float friction);
+/* Study mode (tools/fp32_state_study.py): round X, O, V to fp32 after every write.  NOT the reference's algorithm. */
+void xo_set_state_precision(xo_scene* s, int f32);
 void xo_set_handles(xo_scene* s, uint32_t count, const uint32_t* vertIdx, const float* targetXYZ);
 
 /* Geo3d::Transform, Geo.cpp:358-364. m9 column-major. */

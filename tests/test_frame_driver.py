@@ -98,9 +98,52 @@ def test_frames_stepped_on_device_match_reference_sim(case):
         if case == "lock_right_rotating":
             sx.leftRightSeparation = so.leftRightSeparation = 1.0 - 0.03 * k
         n_ref = sim.update(so, np.float32(dt), np.float32(med), manip=mo)
+        before = geo.info()["kernelLaunches"]
         n = geo.FrameUpdate(sx, np.float32(dt), np.float32(med), state, manip=mx)
         assert n == n_ref
+        # one launch per frame, also while dragging or animating the lock (per-substep rows on the device, xf_substep_varying)
+        assert geo.info()["kernelLaunches"] - before == (1 if n else 0), "frame %d took %d launches for %d substeps" % (
+            k, geo.info()["kernelLaunches"] - before, n)
         Xg, Vg, wg = geo.get_state()
         Xr, Vr, wr = sim.get_state()
         assert np.array_equal(Xg, Xr), "frame %d: max |dX| %.3e" % (k, np.abs(Xg - Xr).max())
         assert np.array_equal(Vg, Vr) and np.array_equal(wg, wr)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR, xf.SCHEDULE_BRICKS])
+def test_substep_varying_equals_single_substeps(schedule):
+    """xf_substep_varying (one launch, per-substep lock transform + manipulator ray) against the same substeps issued one by one
+    on the oracle, with damping sweeps (k_substeps_dataflow_general) and without."""
+    nodes, idx, hint = xf.GenerateTetBlock(6, 3, wonkiness=0.2)
+    for damped in (False, True):
+        geo = xf.GeoLinear3dCuda(nodes, idx, color_hint=hint, schedule=schedule)
+        orc = ob.OracleScene(nodes, idx)
+        orc.set_order(geo.get_order())
+        kw = dict(energy=7, poisson=0.5, lock_right=True)
+        if damped:
+            kw.update(damping=0.004, rayleigh=3, pbd_damping=0.03)
+        sx, so = xf.make_settings(**kw), ob.make_settings(**kw)
+        for s in (sx, so):
+            s.volumeAndTimeCorrectedPbdDamping = 1e-6
+            s.amortizedVolumeAndTimeCorrectedPbdDamping = 7e-6
+        mx, mo = picked_manip(xf.Manipulator, 40), picked_manip(ob.Manipulator, 40)
+        n = 13
+        rng = np.random.default_rng(5)
+        lock = np.zeros((n, 12), dtype=np.float32)
+        dirs = np.zeros((n, 3), dtype=np.float32)
+        for k in range(n):
+            c, s_ = np.float32(np.cos(0.01 * k)), np.float32(np.sin(0.01 * k))
+            lock[k, [0, 1, 4, 5, 10]] = (c * np.float32(0.95), s_ * np.float32(0.95), -s_, c, 1.0)
+            dirs[k] = (0.02 * k / n, 0.05 * k / n, -1.0)
+        dirs += rng.normal(scale=1e-3, size=dirs.shape).astype(np.float32)
+        for k in range(n):
+            so.lockedRightTransform3d[:] = lock[k].tolist()
+            mo.pickDirTarget[:] = dirs[k].tolist()
+            orc.substep(so, np.float32(1 / 3000), 1, manip=mo)
+            so.tickId += 1
+        geo.SubstepVarying(sx, np.float32(1 / 3000), lock, dirs, manip=mx)
+        Xg, Vg, wg = geo.get_state()
+        Xo, Vo, wo = orc.get_state()
+        assert np.array_equal(Xg, Xo) and np.array_equal(Vg, Vo) and np.array_equal(wg, wo), "damped=%s" % damped
+        geo.close()

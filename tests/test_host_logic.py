@@ -22,7 +22,7 @@ def host_scene(nodes, idx, **kw):
 
 def test_library_exports_every_declared_symbol():
     header = open(os.path.join(ROOT, "include", "xpbd_fem_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|uint32_t|void|const char\*)\s+(xf_[a-z_0-9]+)\(", header, flags=re.M))
+    declared = set(re.findall(r"^(?:int|uint32_t|void|float|const char\*|xf_scene\*)\s+(xf_[a-z_0-9]+)\(", header, flags=re.M))
     assert len(declared) >= 20
     L = C.CDLL(xf.LIB_PATH)
     missing = [n for n in sorted(declared) if not hasattr(L, n)]

@@ -132,9 +132,12 @@ _lib = None
 EXPORTS = [
     "xf_last_error", "xf_device_count", "xf_default_create_params", "xf_generate_tet_block", "xf_create", "xf_destroy",
     "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_chain_info", "xf_get_elements", "xf_substep",
-    "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
+    "xf_substep_varying", "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
     "xf_frame_state_init", "xf_frame_update",
+    "xf_sim_create", "xf_sim_destroy", "xf_sim_reset", "xf_sim_add_block", "xf_block_from_settings", "xf_sim_add_block_from_settings",
+    "xf_sim_finish_adding_blocks", "xf_sim_set_geo_offset", "xf_sim_update", "xf_sim_geo_count", "xf_sim_geo", "xf_sim_volume0",
+    "xf_sim_get_frame_state",
     "xf_batch_create", "xf_batch_destroy", "xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count",
     "xf_batch_color_count", "xf_batch_get_order", "xf_batch_set_ground", "xf_batch_substep", "xf_batch_sync",
     "xf_batch_get_state", "xf_batch_set_state", "xf_batch_get_info",
@@ -172,6 +175,7 @@ def lib():
     L.xf_get_chain_info.argtypes = [vp, vp, vp]
     L.xf_get_elements.argtypes = [vp] * 7
     L.xf_substep.argtypes = [vp, vp, vp, f32, u32]
+    L.xf_substep_varying.argtypes = [vp, vp, vp, f32, u32, vp, vp]
     L.xf_sync.argtypes = [vp]
     L.xf_set_ground.argtypes = [vp, i32, f32, f32]
     L.xf_set_handles.argtypes = [vp, u32, vp, vp]
@@ -188,6 +192,22 @@ def lib():
     L.xf_frame_state_init.argtypes = [C.POINTER(FrameState)]
     L.xf_frame_state_init.restype = None
     L.xf_frame_update.argtypes = [vp, vp, vp, f32, f32, C.POINTER(FrameState), C.POINTER(u32)]
+    L.xf_sim_create.argtypes = [C.POINTER(CreateParams), C.POINTER(vp)]
+    L.xf_sim_destroy.argtypes = [vp]
+    L.xf_sim_reset.argtypes = [vp]
+    L.xf_sim_add_block.argtypes = [vp, u32, vp, u32, vp, u32, i32, vp, u32]
+    L.xf_block_from_settings.argtypes = [vp, C.POINTER(u32), C.POINTER(u32), C.POINTER(f32), C.POINTER(f32), C.POINTER(u32)]
+    L.xf_sim_add_block_from_settings.argtypes = [vp, vp]
+    L.xf_sim_finish_adding_blocks.argtypes = [vp, vp]
+    L.xf_sim_set_geo_offset.argtypes = [vp, f32, f32]
+    L.xf_sim_update.argtypes = [vp, vp, vp, i32, f32, f32, C.POINTER(u32)]
+    L.xf_sim_geo_count.argtypes = [vp]
+    L.xf_sim_geo_count.restype = u32
+    L.xf_sim_geo.argtypes = [vp, u32]
+    L.xf_sim_geo.restype = vp
+    L.xf_sim_volume0.argtypes = [vp, u32]
+    L.xf_sim_volume0.restype = f32
+    L.xf_sim_get_frame_state.argtypes = [vp, C.POINTER(FrameState)]
     L.xf_batch_create.argtypes = [C.POINTER(CreateParams), vp, u32, vp, u32, u32, C.POINTER(vp)]
     L.xf_batch_destroy.argtypes = [vp]
     for n in ("xf_batch_scene_count", "xf_batch_vert_count", "xf_batch_element_count", "xf_batch_color_count"):
@@ -317,9 +337,19 @@ class GeoLinear3dCuda:
         self.nT = L.xf_element_count(h)
         self.nColors = L.xf_color_count(h)
 
+    @classmethod
+    def _view(cls, handle):
+        """A scene owned by somebody else (a SimCuda): same methods, close() does not destroy it."""
+        self = cls.__new__(cls)
+        self._h, self._owned = handle, False
+        L = lib()
+        self.nV, self.nT, self.nColors = L.xf_vert_count(handle), L.xf_element_count(handle), L.xf_color_count(handle)
+        return self
+
     def close(self):
         if self._h:
-            lib().xf_destroy(self._h)
+            if getattr(self, "_owned", True):
+                lib().xf_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -338,6 +368,14 @@ class GeoLinear3dCuda:
     def Substep(self, settings, dt, n=1, manip=None):
         """Geo::Substep(settings, manip, dt), n times (asynchronous)."""
         _check(lib().xf_substep(self._h, C.byref(settings), C.byref(manip) if manip is not None else None, float(dt), int(n)))
+
+    def SubstepVarying(self, settings, dt, lock_rows=None, dir_rows=None, manip=None):
+        """n substeps in one launch with a per-substep lock transform (n x 12) and / or manipulator ray (n x 3)."""
+        lock_rows = None if lock_rows is None else np.ascontiguousarray(lock_rows, dtype=np.float32).reshape(-1, 12)
+        dir_rows = None if dir_rows is None else np.ascontiguousarray(dir_rows, dtype=np.float32).reshape(-1, 3)
+        n = (lock_rows if lock_rows is not None else dir_rows).shape[0]
+        _check(lib().xf_substep_varying(self._h, C.byref(settings), C.byref(manip) if manip is not None else None, float(dt), int(n), _vp(lock_rows),
+                                        _vp(dir_rows)))
 
     def Sync(self):
         _check(lib().xf_sync(self._h))
@@ -446,6 +484,76 @@ class GeoLinear3dCuda:
 
     def set_state_async(self, X_ptr, V_ptr):
         _check(lib().xf_set_state_async(self._h, X_ptr, V_ptr))
+
+
+class SimCuda:
+    """The reference's Sim (Demo.h:18-52): several Geos under one Settings block and one frame clock (xf_sim_*)."""
+
+    def __init__(self, device=0, precision=PRECISION_EXACT, schedule=SCHEDULE_AUTO, stream=None):
+        p = CreateParams()
+        lib().xf_default_create_params(C.byref(p))
+        p.device, p.precision, p.schedule, p.stream = device, precision, schedule, stream
+        h = C.c_void_p()
+        self._h = None
+        _check(lib().xf_sim_create(C.byref(p), C.byref(h)))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            lib().xf_sim_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def Reset(self):
+        _check(lib().xf_sim_reset(self._h))
+
+    def AddBlock(self, nodes, idx_stream, auto_resize=False, color_hint=None):
+        nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
+        idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
+        hint = None if color_hint is None else np.ascontiguousarray(color_hint, dtype=np.uint32)
+        _check(lib().xf_sim_add_block(self._h, Element_T4, _vp(nodes), nodes.size, _vp(idx_stream), idx_stream.size, 1 if auto_resize else 0,
+                                      _vp(hint), 0 if hint is None else hint.size))
+
+    def AddBlockFromSettings(self, settings):
+        _check(lib().xf_sim_add_block_from_settings(self._h, C.byref(settings)))
+
+    def FinishAddingBlocks(self, settings):
+        _check(lib().xf_sim_finish_adding_blocks(self._h, C.byref(settings)))
+
+    def SetGeoOffset(self, x, y):
+        _check(lib().xf_sim_set_geo_offset(self._h, float(x), float(y)))
+
+    def Update(self, settings, dt, median_frame_time, manip=None, picked_geo=-1):
+        n = C.c_uint32(0)
+        _check(lib().xf_sim_update(self._h, C.byref(settings), C.byref(manip) if manip is not None else None, int(picked_geo), float(dt),
+                                   float(median_frame_time), C.byref(n)))
+        return n.value
+
+    def geo_count(self):
+        return int(lib().xf_sim_geo_count(self._h))
+
+    def geo(self, i):
+        """Geo i as a (non-owning) GeoLinear3dCuda view."""
+        h = lib().xf_sim_geo(self._h, i)
+        if not h:
+            raise IndexError(i)
+        return GeoLinear3dCuda._view(C.c_void_p(h))
+
+    def volume0(self, i):
+        return float(lib().xf_sim_volume0(self._h, i))
+
+
+def block_from_settings(settings):
+    """(width, height, scaleX, scaleY, pattern) of the block Demo::UpdateSettings builds for these settings (Demo.cpp:289-318)."""
+    w, h, pat = C.c_uint32(), C.c_uint32(), C.c_uint32()
+    sx, sy = C.c_float(), C.c_float()
+    _check(lib().xf_block_from_settings(C.byref(settings), C.byref(w), C.byref(h), C.byref(sx), C.byref(sy), C.byref(pat)))
+    return w.value, h.value, sx.value, sy.value, pat.value
 
 
 class GeoBatchCuda:

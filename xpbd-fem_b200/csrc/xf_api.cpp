@@ -68,6 +68,8 @@ struct xf_scene {
 	uint64_t launches = 0;
 	uint32_t lastKernel = 0;  // xf_kernel_id of the last stepping launch
 	uint64_t vEpoch = 1;      // substeps stepped by k_substeps_dataflow_general so far (V-record tags)
+	float* dVary = nullptr;   // per-substep parameter rows of xf_substep_varying (kVaryFloats floats each)
+	size_t dVaryRows = 0;
 	// extensions
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
@@ -89,7 +91,7 @@ void FreeDevice(xf_scene* s) {
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
 	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
-		             d.barrier, s->dPackX, s->dPackV, s->dPackW };
+		             d.barrier, s->dPackX, s->dPackV, s->dPackW, s->dVary };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->stallWord) { cudaFreeHost((void*)s->stallWord); }
 	if (s->ownStream && s->stream) { cudaStreamDestroy(s->stream); }
@@ -420,25 +422,22 @@ int xf_get_elements(const xf_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, f
 	return XF_OK;
 }
 
-int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, float dt, uint32_t n) {
-	int rc = NeedDevice(s);
-	if (rc != XF_OK) { return rc; }
-	if (!st) { return Fail(XF_ERR_INVALID, "null settings"); }
-	if (n == 0) { return XF_OK; }
-	SubstepParams p;
-	rc = BuildParams(s, st, manip, dt, &p);
-	if (rc != XF_OK) { return rc; }
+// Launches n substeps with the prepared parameters (p.vary, if set, holds n rows; a call that is split into several launches
+// advances it).
+static int LaunchSubsteps(xf_scene* s, SubstepParams& p, uint32_t firstTick, uint32_t n) {
 	const bool exact = s->precision == XF_PRECISION_EXACT;
 	// the barrier-free schedule covers everything but in-constraint Rayleigh damping (Paper / Limit read O of other threads' vertices)
 	const bool inConstraintDamping = p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST;
 	const bool plainSweep = !inConstraintDamping && !p.doDamp && !p.doPbdDamp && p.volumePasses == 0;
 	const bool generalOk = !inConstraintDamping && s->dev.eRank && !s->dev.chained && s->dev.groupSize <= 1 && !getenv("XF_NO_DATAFLOW_GENERAL");
+	const float* vary0 = p.vary;
 	if (s->schedule == XF_SCHEDULE_DATAFLOW && (plainSweep || generalOk)) {
 		const uint32_t stride = plainSweep ? p.nColors + 1u : DataflowGeneralStride(p);
 		const uint32_t maxPerLaunch = std::max(1u, (0x00ffffffu - 2u) / stride); // tags of one launch must not wrap onto the stale ones
 		for (uint32_t done = 0; done < n;) {
 			const uint32_t m = std::min(n - done, maxPerLaunch);
-			p.tickId = st->tickId + done;
+			p.tickId = firstTick + done;
+			p.vary = vary0 ? vary0 + (size_t)kVaryFloats * done : nullptr;
 			s->lastKernel = !plainSweep ? XF_KERNEL_DATAFLOW_GENERAL
 			                            : (s->dev.groupSize > 1 ? XF_KERNEL_CLUSTER : (s->dev.chained ? XF_KERNEL_CHAIN : XF_KERNEL_DATAFLOW));
 			if (!plainSweep) {
@@ -471,6 +470,75 @@ int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, 
 		XF_CUDA(LaunchSubstepsPerColor(s->dev, p, exact, n, s->stream, &s->launches));
 	}
 	return XF_OK;
+}
+
+int xf_substep(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, float dt, uint32_t n) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!st) { return Fail(XF_ERR_INVALID, "null settings"); }
+	if (n == 0) { return XF_OK; }
+	SubstepParams p;
+	rc = BuildParams(s, st, manip, dt, &p);
+	if (rc != XF_OK) { return rc; }
+	return LaunchSubsteps(s, p, st->tickId, n);
+}
+
+// n substeps in ONE launch while the right-side lock transform and / or the manipulator ray change from substep to substep
+// (what Sim::Update does between its Substep calls, Demo.cpp:67-90).  lockT3d: n x 12 floats (Settings::lockedRightTransform3d
+// of every substep) or NULL; pickDirTarget: n x 3 floats (Manipulator::pickDirTarget of every substep) or NULL.  Everything
+// else comes from *st / *manip; tickId advances by one per substep as in xf_substep.  Bit-identical to n calls of
+// xf_substep(.., 1) with the same values.
+int xf_substep_varying(xf_scene* s, const xf_settings* st, const xf_manipulator* manip, float dt, uint32_t n, const float* lockT3d,
+                       const float* pickDirTarget) {
+	int rc = NeedDevice(s);
+	if (rc != XF_OK) { return rc; }
+	if (!st) { return Fail(XF_ERR_INVALID, "null settings"); }
+	if (n == 0) { return XF_OK; }
+	const bool picked = manip && manip->picked;
+	const bool supported = s->schedule == XF_SCHEDULE_DATAFLOW || s->schedule == XF_SCHEDULE_PERSISTENT;
+	if ((!lockT3d && !(pickDirTarget && picked)) || !supported) {
+		if (!lockT3d && !(pickDirTarget && picked)) { return xf_substep(s, st, manip, dt, n); }
+		// schedules without per-substep rows: one call per substep (same values, same bits)
+		xf_settings stK = *st;
+		xf_manipulator mK;
+		if (manip) { mK = *manip; }
+		for (uint32_t k = 0; k < n; k++) {
+			if (lockT3d) { memcpy(stK.lockedRightTransform3d, lockT3d + 12 * (size_t)k, sizeof(float) * 12); }
+			if (manip && pickDirTarget) { memcpy(mK.pickDirTarget, pickDirTarget + 3 * (size_t)k, sizeof(float) * 3); }
+			stK.tickId = st->tickId + k;
+			rc = xf_substep(s, &stK, manip ? &mK : nullptr, dt, 1);
+			if (rc != XF_OK) { return rc; }
+		}
+		return XF_OK;
+	}
+	SubstepParams p;
+	rc = BuildParams(s, st, manip, dt, &p);
+	if (rc != XF_OK) { return rc; }
+	// per-substep rows: the same host arithmetic as BuildParams, once per substep
+	std::vector<float> rows((size_t)kVaryFloats * n, 0.0f);
+	xf_settings stK = *st;
+	xf_manipulator mK;
+	if (manip) { mK = *manip; }
+	for (uint32_t k = 0; k < n; k++) {
+		if (lockT3d) { memcpy(stK.lockedRightTransform3d, lockT3d + 12 * (size_t)k, sizeof(float) * 12); }
+		if (manip && pickDirTarget) { memcpy(mK.pickDirTarget, pickDirTarget + 3 * (size_t)k, sizeof(float) * 3); }
+		SubstepParams pk;
+		std::string err;
+		rc = FillSubstepParams(&stK, manip ? &mK : nullptr, dt, s->mesh, &pk, &err);
+		if (rc != XF_OK) { return Fail(rc, err); }
+		memcpy(&rows[(size_t)kVaryFloats * k], pk.lockT, sizeof(float) * 12);
+		memcpy(&rows[(size_t)kVaryFloats * k + 12], pk.manipTarget, sizeof(float) * 3);
+	}
+	if (s->dVaryRows < n) {
+		XF_CUDA(cudaStreamSynchronize(s->stream)); // a launch in flight may still read the old rows
+		if (s->dVary) { cudaFree(s->dVary); s->dVary = nullptr; }
+		s->dVaryRows = std::max<size_t>(n, 512);
+		XF_CUDA(cudaMalloc((void**)&s->dVary, sizeof(float) * kVaryFloats * s->dVaryRows));
+	}
+	// stream-ordered after the previous launch; the source is pageable memory, so the runtime has copied it out when the call returns
+	XF_CUDA(cudaMemcpyAsync(s->dVary, rows.data(), sizeof(float) * rows.size(), cudaMemcpyHostToDevice, s->stream));
+	p.vary = s->dVary;
+	return LaunchSubsteps(s, p, st->tickId, n);
 }
 
 int xf_sync(xf_scene* s) {

@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow(const DeviceScene 
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs, s > 0 ? VaryRow(p, s - 1u) : nullptr);
 			}
 		}
 		if (closing) { break; }
@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_cluster(const DeviceScene s
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs, s > 0 ? VaryRow(p, s - 1u) : nullptr);
 			}
 		}
 		if (closing) { break; }
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_chain(const DeviceScene sc,
 			const unsigned mask = __ballot_sync(0xffffffffu, has);
 			if (has) {
 				const uint32_t expectTag = (stageBase - stride + (uint32_t)__ldg(sc.lastCode + i)) << 8;
-				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs, s > 0 ? VaryRow(p, s - 1u) : nullptr);
 			}
 		}
 		if (closing) { break; }

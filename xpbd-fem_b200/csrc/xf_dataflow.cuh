@@ -23,7 +23,7 @@ constexpr uint32_t kVerMask = 0xffffff00u;
 // every mesh size.  With a vote over the lanes that have work, the warp leaves the loop as one.
 template <bool EXACT>
 __device__ __forceinline__ bool DataflowVertex(const DeviceScene& sc, const SubstepParams& p, uint32_t i, unsigned mask, bool doPost, bool doPredict,
-                                               bool wait, uint32_t expectTag, uint32_t newTag, uint32_t sleepNs) {
+                                               bool wait, uint32_t expectTag, uint32_t newTag, uint32_t sleepNs, const float* vary = nullptr) {
 	VertexRegs v = LoadVertex(sc.Xw, i);
 	if (wait) {
 		for (uint32_t spins = 0;; spins++) {
@@ -34,7 +34,7 @@ __device__ __forceinline__ bool DataflowVertex(const DeviceScene& sc, const Subs
 			if (!ok) { v = LoadVertex(sc.Xw, i); }
 		}
 	}
-	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict);
+	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict, 0.0, vary);
 	v.flags = (v.flags & 0xffu) | newTag;
 	StoreVertex(sc.Xw, i, v);
 	return true;

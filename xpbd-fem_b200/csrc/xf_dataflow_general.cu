@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow_general(const Devi
 			if (!anyDamp) {
 				const uint32_t lc = __ldg(sc.lastCode + i);
 				const uint32_t expectTag = (lc ? prevLast + lc : stageBase - stride) << 8;
-				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs);
+				dead = !DataflowVertex<EXACT>(sc, p, i, mask, s > 0, !closing, s > 0, expectTag, stageBase << 8, sleepNs, s > 0 ? VaryRow(p, s - 1u) : nullptr);
 			} else {
 				// predict only; the damping sweeps of the previous substep must be through with this vertex (they read its position)
 				if (s > 0) {
@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow_general(const Devi
 				if (!ok) { v = LoadVertex(sc.Xw, i); }
 			}
 			if (dead) { continue; }
-			VertexPhaseBody<EXACT>(sc, p, i, v, true, false, __longlong_as_double((long long)vBase));
+			VertexPhaseBody<EXACT>(sc, p, i, v, true, false, __longlong_as_double((long long)vBase), VaryRow(p, s));
 			v.flags = (v.flags & 0xffu) | (postStage << 8);
 			StoreVertex(sc.Xw, i, v);
 		}

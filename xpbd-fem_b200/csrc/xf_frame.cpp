@@ -4,6 +4,7 @@
 // Host-only arithmetic, compiled with -ffp-contract=off so every derived constant matches the reference's bits.
 #include <cmath>
 #include <cstring>
+#include <vector>
 
 #include "xf_scene.h"
 
@@ -15,9 +16,12 @@ extern "C" void xf_frame_state_init(xf_frame_state* st) { // Sim::Reset, Demo.cp
 	st->rightRotationTheta = 0.0f;
 }
 
-extern "C" int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipulator* manip, float dt, float medianFrameTime, xf_frame_state* st,
-                               uint32_t* outSubsteps) {
-	// scene == nullptr: bookkeeping only (substep count, derived constants, lock / manipulator animation) - lets the
+// Sim::Update for `count` Geos that share the Settings (Demo.cpp:86-88: every substep steps every geo; here every geo gets its
+// frame's substeps in one launch - the geos are independent, so the order of (geo, substep) pairs does not matter).  The
+// manipulator acts on geo `pickedGeo` only (Manipulator::pickedGeo, Geo.cpp:334).
+int xf::FrameUpdateGeos(xf_scene* const* scenes, uint32_t count, int pickedGeo, xf_settings* settings, xf_manipulator* manip, float dt,
+                        float medianFrameTime, xf_frame_state* st, uint32_t* outSubsteps) {
+	// count == 0: bookkeeping only (substep count, derived constants, lock / manipulator animation) - lets the
 	// host logic be tested without a device; nothing is stepped.
 	if (!settings || !st) { return xf::Fail(XF_ERR_INVALID, "null argument"); }
 	const float kSpacing = (20.0f / 100.0f) / (float)(31); // Demo.cpp:16
@@ -56,12 +60,18 @@ extern "C" int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipu
 			for (int k = 0; k < 3; k++) { manip->pickDirTarget[k] = manip->pickDirOld[k] * (1.0f - a) + manip->pickDir[k] * a; }
 		}
 		if (substeps > 0) {
-			int rc = scene ? xf_substep(scene, settings, manip, sdt, substeps) : XF_OK;
-			if (rc != XF_OK) { return rc; }
+			for (uint32_t g = 0; g < count; g++) {
+				int rc = xf_substep(scenes[g], settings, (int)g == pickedGeo ? manip : nullptr, sdt, substeps);
+				if (rc != XF_OK) { return rc; }
+			}
 			st->tickId += substeps;
 			settings->tickId = st->tickId - 1; // the value the reference leaves in its Settings after the loop
 		}
-	} else {
+	} else if (substeps > 0) {
+		// the lock transform and the manipulator ray change every substep: their per-substep values go to the device as arrays and
+		// the whole frame is still ONE launch (xf_substep_varying)
+		std::vector<float> lockRows(lockRight ? 12 * (size_t)substeps : 0), dirRows(manip ? 3 * (size_t)substeps : 0);
+		const uint32_t firstTick = st->tickId;
 		for (uint32_t substep = 0; substep < substeps; substep++) {
 			if (lockRight) { // Demo.cpp:69-80
 				const float a = (float)substep / (float)substeps;
@@ -84,17 +94,29 @@ extern "C" int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipu
 				T3[0] = T[0]; T3[1] = T[1]; T3[2] = 0.0f;
 				T3[4] = T[2]; T3[5] = T[3]; T3[6] = 0.0f;
 				T3[8] = 0.0f; T3[9] = 0.0f; T3[10] = 1.0f;
+				memcpy(&lockRows[12 * (size_t)substep], T3, sizeof(float) * 12);
 			}
-			settings->tickId = st->tickId;
 			if (manip) { // Demo.cpp:84
 				const float a = (float)(substep + 1) / (float)substeps;
 				for (int k = 0; k < 3; k++) { manip->pickDirTarget[k] = manip->pickDirOld[k] * (1.0f - a) + manip->pickDir[k] * a; }
+				memcpy(&dirRows[3 * (size_t)substep], manip->pickDirTarget, sizeof(float) * 3);
 			}
-			int rc = scene ? xf_substep(scene, settings, manip, sdt, 1) : XF_OK;
-			if (rc != XF_OK) { return rc; }
 			++st->tickId;
 		}
+		settings->tickId = firstTick;
+		for (uint32_t g = 0; g < count; g++) {
+			const bool mine = (int)g == pickedGeo && manip;
+			int rc = xf_substep_varying(scenes[g], settings, mine ? manip : nullptr, sdt, substeps, lockRight ? lockRows.data() : nullptr,
+			                            mine ? dirRows.data() : nullptr);
+			if (rc != XF_OK) { return rc; }
+		}
+		settings->tickId = st->tickId - 1; // the value the reference leaves in its Settings after the loop
 	}
 	st->leftRightSeparationOld = settings->leftRightSeparation;
 	return XF_OK;
+}
+
+extern "C" int xf_frame_update(xf_scene* scene, xf_settings* settings, xf_manipulator* manip, float dt, float medianFrameTime, xf_frame_state* st,
+                               uint32_t* outSubsteps) {
+	return xf::FrameUpdateGeos(&scene, scene ? 1u : 0u, 0, settings, manip, dt, medianFrameTime, st, outSubsteps);
 }

@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(XF_PERSIST_THREADS, XF_PERSIST_MIN_BLOCKS) k_s
 		// damping sweep already closed it) + predict
 		if (p.colorStart[0] + slot < p.colorStart[1]) { SweepLoad<0, ENERGY, EXACT>(sc, p.colorStart[0] + slot, rec); }
 		const bool fusePost = (s > 0) && !anyDamp;
-		for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, fusePost, true); }
+		for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, fusePost, true, fusePost ? VaryRow(p, s - 1u) : nullptr); }
 		grid.sync();
 		for (uint32_t c = 0; c < nC; c++) {
 			const bool last = c + 1 == nC;
@@ -134,7 +134,7 @@ __global__ void __launch_bounds__(XF_PERSIST_THREADS, XF_PERSIST_MIN_BLOCKS) k_s
 			}
 		}
 		if (anyDamp) {
-			for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, true, false); }
+			for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, true, false, VaryRow(p, s)); }
 			grid.sync();
 			uint32_t lo, hi;
 			DampSlice(p, sc.nT, p.tickId + s, lo, hi);
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(XF_PERSIST_THREADS, XF_PERSIST_MIN_BLOCKS) k_s
 		}
 	}
 	if (!anyDamp && nSubsteps > 0) {
-		for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, true, false); }
+		for (uint32_t i = gtid; i < sc.nV; i += gsize) { VertexPhase<EXACT>(sc, p, i, true, false, VaryRow(p, nSubsteps - 1u)); }
 	}
 }
 

@@ -26,9 +26,13 @@ __device__ __forceinline__ void DragTowards(VertexRegs& v, const float* target, 
 // for the right lock) are read/written in global memory.  The caller stores `v` back to wherever it lives.
 // `vTag` goes into the spare fourth word of the V record: the barrier-free kernels with damping sweeps version V records
 // the way they version position records (xf_dataflow_general.cu); 0.0 everywhere else.
+// `vary`: this substep's row of SubstepParams::vary (lock transform, manipulator target), or nullptr.
+__device__ __forceinline__ const float* VaryRow(const SubstepParams& p, uint32_t substep) {
+	return p.vary ? p.vary + (size_t)kVaryFloats * substep : nullptr;
+}
 template <bool EXACT>
 __device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const SubstepParams& p, uint32_t i, VertexRegs& v, bool doPost, bool doPredict,
-                                                double vTag = 0.0) {
+                                                double vTag = 0.0, const float* vary = nullptr) {
 	typedef Op<EXACT> O;
 	double o[3], vel[3];
 	LoadD3(sc.O, i, o);
@@ -52,14 +56,20 @@ __device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const Sub
 			float x0[3] = { __double2float_rn(x0d[0]), __double2float_rn(x0d[1]), __double2float_rn(x0d[2]) };
 #pragma unroll
 			for (int r = 0; r < 3; r++) {
-				float t = O::dot(p.lockT[0 + r], p.lockT[4 + r], p.lockT[8 + r], x0[0], x0[1], x0[2]);
+				const float t0 = vary ? __ldg(vary + 0 + r) : p.lockT[0 + r], t1 = vary ? __ldg(vary + 4 + r) : p.lockT[4 + r],
+				            t2 = vary ? __ldg(vary + 8 + r) : p.lockT[8 + r];
+				float t = O::dot(t0, t1, t2, x0[0], x0[1], x0[2]);
 				double q = (double)O::add(p.origin[r], t);
 				v.x[r] = q;
 				o[r] = q;
 			}
 			v.w = 0.0f;
 		}
-		if (p.manipOn && i == p.manipIdx) { DragTowards<EXACT>(v, p.manipTarget, p.c18); }
+		if (p.manipOn && i == p.manipIdx) {
+			const float target[3] = { vary ? __ldg(vary + 12) : p.manipTarget[0], vary ? __ldg(vary + 13) : p.manipTarget[1],
+				                      vary ? __ldg(vary + 14) : p.manipTarget[2] };
+			DragTowards<EXACT>(v, target, p.c18);
+		}
 		for (uint32_t h = 0; h < p.handleCount; h++) {
 			if (p.handleIdx[h] == i) { DragTowards<EXACT>(v, p.handleTarget[h], p.c18); }
 		}
@@ -86,9 +96,10 @@ __device__ __forceinline__ void VertexPhaseBody(const DeviceScene& sc, const Sub
 }
 
 template <bool EXACT>
-__device__ __forceinline__ void VertexPhase(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict) {
+__device__ __forceinline__ void VertexPhase(const DeviceScene& sc, const SubstepParams& p, uint32_t i, bool doPost, bool doPredict,
+                                            const float* vary = nullptr) {
 	VertexRegs v = LoadVertex(sc.Xw, i);
-	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict);
+	VertexPhaseBody<EXACT>(sc, p, i, v, doPost, doPredict, 0.0, vary);
 	StoreVertex(sc.Xw, i, v);
 }
 

@@ -644,6 +644,7 @@ int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float 
 	}
 	p->nColors = (uint32_t)mesh.colorStart.size() - 1;
 	for (size_t c = 0; c < mesh.colorStart.size(); c++) { p->colorStart[c] = mesh.colorStart[c]; }
+	p->vary = nullptr;
 	return XF_OK;
 }
 

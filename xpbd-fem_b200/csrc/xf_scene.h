@@ -144,7 +144,12 @@ struct SubstepParams {
 	float handleTarget[kMaxHandles][3];
 	uint32_t colorStart[kMaxColors + 1];
 	uint32_t nColors;
+	// Parameters that change from substep to substep inside one call (xf_substep_varying: an animated right-side lock, a moving
+	// manipulator ray - Sim::Update's per-substep work, Demo.cpp:67-90): kVaryFloats floats per substep in device memory,
+	// {lockT[12], manipTarget[3], pad}; nullptr = lockT / manipTarget above hold for the whole call.
+	const float* vary;
 };
+constexpr int kVaryFloats = 16;
 
 // Per-scene constants of a batched call (xf_batch.cu): the scalar part of SubstepParams.  The element math is
 // templated on the parameter type and only touches fields that exist in both.
@@ -229,6 +234,10 @@ uint64_t ChainInfo(const HostMesh& mesh, const std::vector<uint32_t>& order, con
 void PackElements(const HostMesh& mesh, const std::vector<uint32_t>& elems, const uint32_t* localIdx, PackedElements* out);
 int FillSubstepParams(const xf_settings* st, const xf_manipulator* manip, float dt, const HostMesh& mesh, SubstepParams* p,
                       std::string* err);
+
+// Sim::Update over several scenes (xf_frame.cpp); xf_frame_update and xf_sim_update are thin wrappers
+int FrameUpdateGeos(xf_scene* const* scenes, uint32_t count, int pickedGeo, xf_settings* settings, xf_manipulator* manip, float dt,
+                    float medianFrameTime, xf_frame_state* state, uint32_t* outSubsteps);
 
 // error reporting shared by the ABI translation units (xf_api.cpp)
 int Fail(int status, const std::string& msg);
