@@ -359,6 +359,9 @@ int xf_part_get_info(const xf_partition* part, uint64_t* launches, uint64_t* epo
  *   waiting warp gives up, 2 = corrupt the last-writer code of device vertex 0 (stall-report test).
  * xf_debug_barrier_us: cost of a bare grid barrier (several implementations). */
 int xf_debug_l2_bandwidth(int device, int mode, uint64_t bytes, uint32_t passes, int reps, int blocksPerSm, double* outGBs);
+/* cycles of (mode 0) one element solve of a lone warp, (mode 1) one record hand-off between two SMs, (mode 2) one dependent
+ * 256-bit L2 load: the decomposition of a stage of the barrier-free sweep (xf_probe_latency.cu) */
+int xf_debug_stage_latency(int device, int mode, uint32_t iterations, double* outCycles);
 int xf_debug_torn_records(int device, int remoteDevice, uint32_t nRecords, uint32_t rounds, uint64_t* outReads, uint64_t* outTorn);
 int xf_debug_scene_knob(xf_scene* scene, int knob, uint32_t value);
 int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int threads, uint32_t iterations, float* outUsPerBarrier);

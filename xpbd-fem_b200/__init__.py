@@ -146,7 +146,7 @@ EXPORTS = [
     "xf_part_get_local_elements", "xf_part_get_peers", "xf_part_get_halo", "xf_part_get_order", "xf_part_get_global_color_start",
     "xf_part_get_initial", "xf_part_get_dataflow_codes", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
     "xf_part_get_state", "xf_part_get_info",
-    "xf_debug_l2_bandwidth", "xf_debug_torn_records", "xf_debug_scene_knob", "xf_debug_barrier_us",
+    "xf_debug_l2_bandwidth", "xf_debug_stage_latency", "xf_debug_torn_records", "xf_debug_scene_knob", "xf_debug_barrier_us",
 ]
 
 
@@ -268,6 +268,14 @@ def l2_bandwidth(device=0, mode=0, mbytes=16, passes=200, reps=5, blocks_per_sm=
     """GB/s of an L2-resident streaming copy (mode 0, read + write bytes) or read (mode 1); see xf_debug_l2_bandwidth."""
     out = C.c_double(0.0)
     _check(lib().xf_debug_l2_bandwidth(device, mode, int(mbytes) << 20, passes, reps, blocks_per_sm, C.byref(out)))
+    return out.value
+
+
+def stage_latency(device=0, mode=0, iterations=2000):
+    """Cycles per element solve (0), per record hand-off between two SMs (1), per dependent 256-bit L2 load (2)."""
+    out = C.c_double(0.0)
+    lib().xf_debug_stage_latency.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_double)]
+    _check(lib().xf_debug_stage_latency(device, mode, iterations, C.byref(out)))
     return out.value
 
 
