@@ -101,6 +101,15 @@ typedef struct xf_settings {
 	uint32_t _pad2[3];
 } xf_settings;
 
+/* How xf_part_create splits the elements of one mesh over the ranks. */
+typedef enum xf_partition_method {
+	XF_PARTITION_SLABS = 0, /* contiguous chunks of the order "rest-pose centroid x": slabs for MeshGen blocks; a vertex has at most
+	                           two copies, so the barrier-free cross-GPU schedule (k_part_dataflow) applies */
+	XF_PARTITION_GRAPH = 1  /* greedy graph growing over the element adjacency graph (breadth-first from peripheral seeds, balanced
+	                           part sizes): connected parts for irregular meshes; vertices may have copies on several ranks, which
+	                           runs on the flag protocol (phases ordered by system-scope flags) */
+} xf_partition_method;
+
 /* Flat mirror of Manipulator.h:9-13.  picked != 0 <=> `manip.pickedGeo == this` (Geo.cpp:334). */
 typedef struct xf_manipulator {
 	float pos[3], manipPlaneNormal[3], pick0[3], pickDir[3], pickDirOld[3], pickDirTarget[3];
@@ -121,8 +130,9 @@ typedef enum xf_schedule {
 	XF_SCHEDULE_BRICKS = 3,           /* PERSISTENT + vertices private to a CTA's brick of elements kept in shared memory */
 	XF_SCHEDULE_DATAFLOW = 4          /* one co-resident launch, NO barriers: vertex records carry the stage that wrote them and
 	                                     every element re-gathers until its four records carry the expected stage.  Same serial
-	                                     order and bits as the others.  Calls that need volume passes, damping sweeps or
-	                                     in-constraint Rayleigh damping run as XF_SCHEDULE_PERSISTENT. */
+	                                     order and bits as the others, also with volume passes and post-solve damping sweeps
+	                                     (k_substeps_dataflow_general).  Only calls with in-constraint Rayleigh damping
+	                                     (Paper / Limit) run as XF_SCHEDULE_PERSISTENT. */
 } xf_schedule;
 
 /* Clustered colouring: consecutive stream elements that share vertices and touch at most 8 distinct ones (MeshGen: the six
@@ -152,7 +162,8 @@ typedef struct xf_create_params {
 	const uint32_t* colorHint; /* optional: colour per element (in stream order); validated, never trusted */
 	uint32_t colorHintCount;   /* number of entries in colorHint (must equal the element count) */
 	uint32_t grouping;         /* xf_grouping */
-	uint32_t _reserved[4];
+	uint32_t partition;      /* xf_part_create only: xf_partition_method */
+	uint32_t _reserved[3];
 } xf_create_params;
 
 typedef struct xf_scene xf_scene;

@@ -414,6 +414,19 @@ class OracleScene:
                                  _vp(out["volume"]), _vp(out["area"]))
         return out
 
+    def copy_elements_from(self, full, elems, rest=None):
+        """This scene is the sub-mesh `elems` (element ids of `full`, in this scene's element order) of `full`: take its element
+        constants (and, with `rest`, its rest positions) instead of the ones re-derived from this scene's own coordinates."""
+        el = full.get_elements()
+        vp = C.c_void_p
+        self.lib.xo_set_elements.argtypes = [vp] * 6
+        self.lib.xo_set_rest.argtypes = [vp, vp]
+        sub = {k: np.ascontiguousarray(el[k][elems]) for k in ("Qi", "QQ", "QR", "volume", "area")}
+        self.lib.xo_set_elements(self.h, _vp(sub["Qi"]), _vp(sub["QQ"]), _vp(sub["QR"]), _vp(sub["volume"]), _vp(sub["area"]))
+        if rest is not None:
+            rest = np.ascontiguousarray(rest, dtype=np.float64)
+            self.lib.xo_set_rest(self.h, _vp(rest))
+
     def transform(self, m9):
         m9 = np.ascontiguousarray(m9, dtype=np.float32).reshape(9)
         self.lib.xo_transform(self.h, _vp(m9))

@@ -335,6 +335,22 @@ void xo_get_elements(const xo_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, 
 		if (area) { area[e] = t->surfaceArea; }
 	}
 }
+/* Test plumbing for sub-meshes of a larger scene (tests/part_worker.py): element constants and rest positions taken from the
+ * scene they were cut from instead of being re-derived from rounded coordinates. */
+void xo_set_elements(xo_scene* s, const float* Qi9, const float* QQ3, const float* QR3, const float* volume, const float* area) {
+	for (uint32_t e = 0; e < s->nT; e++) {
+		xo_tet* t = &s->t[e];
+		for (int c = 0; c < 3; c++) { for (int r = 0; r < 3; r++) { t->Qi[c][r] = Qi9[9 * e + 3 * c + r]; } }
+		for (int j = 0; j < 3; j++) { t->QQ[j] = QQ3[3 * e + j]; t->QR[j] = QR3[3 * e + j]; }
+		t->volume = volume[e];
+		t->surfaceArea = area[e];
+	}
+}
+void xo_set_rest(xo_scene* s, const double* X0) {
+	memcpy(s->X0, X0, sizeof(double) * 3 * s->nV);
+	memcpy(s->X, X0, sizeof(double) * 3 * s->nV);
+	memcpy(s->O, X0, sizeof(double) * 3 * s->nV);
+}
 void xo_set_flags(xo_scene* s, const uint8_t* flags) { memcpy(s->flags, flags, s->nV); }
 void xo_get_origin(const xo_scene* s, float* o) { o[0] = s->origin[0]; o[1] = s->origin[1]; o[2] = s->origin[2]; }
 

@@ -52,6 +52,8 @@ void xo_set_order(xo_scene* s, const uint32_t* order);
 void xo_get_state(const xo_scene* s, double* X, double* V, float* w);
 void xo_set_state(xo_scene* s, const double* X, const double* V, const float* w);
 void xo_get_rest(const xo_scene* s, double* X0, double* O, uint8_t* flags);
+void xo_set_elements(xo_scene* s, const float* Qi9, const float* QQ3, const float* QR3, const float* volume, const float* area);
+void xo_set_rest(xo_scene* s, const double* X0);
 void xo_get_elements(const xo_scene* s, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* area);
 void xo_get_origin(const xo_scene* s, float* o);
 

@@ -26,20 +26,30 @@ ap.add_argument("--substeps", type=int, default=12)
 ap.add_argument("--no-hint", action="store_true")
 ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--time-substeps", type=int, default=0)
-ap.add_argument("--schedule", choices=["dataflow", "persistent", "per_color"], default="dataflow")
+ap.add_argument("--schedule", choices=["auto", "dataflow", "persistent", "per_color"], default="dataflow")
+ap.add_argument("--partition", choices=["slabs", "graph"], default="slabs")
+ap.add_argument("--mesh", choices=["block", "armadillo"], default="block", help="armadillo: the reference's asset (needs oracle/_ref)")
 a = ap.parse_args()
 xf = load_package()
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 DT = np.float32(1.0 / 3000.0)
-nodes, idx, hint = xf.GenerateTetBlock(a.dims[0], a.dims[1], wonkiness=a.wonk, pattern=a.pattern)
-hint = None if (a.no_hint or a.pattern != 0) else hint
+AUTO_RESIZE = False
+if a.mesh == "armadillo":  # Demo::UpdateSettings' Armadillo path: autoResize = true, density 2 (Demo.cpp:123, 336)
+    from oracle import bindings as ob_mesh
+    nodes, idx = ob_mesh.RefScene.armadillo().get_mesh()
+    hint, AUTO_RESIZE = None, True
+else:
+    nodes, idx, hint = xf.GenerateTetBlock(a.dims[0], a.dims[1], wonkiness=a.wonk, pattern=a.pattern)
+    hint = None if (a.no_hint or a.pattern != 0) else hint
+PARTITION = {"slabs": xf.PARTITION_SLABS, "graph": xf.PARTITION_GRAPH}[a.partition]
+DENSITY = 2.0 if AUTO_RESIZE else 1.0
 kw = dict(energy=a.energy, simultaneous=not a.serial, poisson=a.poisson)
 
 
 def reference_state(order, n):
     from oracle import bindings as ob
-    o = ob.OracleScene(nodes, idx)
+    o = ob.OracleScene(nodes, idx, DENSITY, AUTO_RESIZE)
     o.set_order(order)
     o.substep(ob.make_settings(**kw), DT, n)
     return o.get_state()
@@ -48,7 +58,7 @@ def reference_state(order, n):
 if a.mode == "emulate":
     from oracle import bindings as ob
     dist.init_process_group("gloo")
-    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=-1, color_hint=hint)
+    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=-1, color_hint=hint, partition=PARTITION, density=DENSITY, auto_resize=AUTO_RESIZE)
     l2g = part.local_verts()
     elems, cs = part.local_elements()
     peers = part.peers()
@@ -58,9 +68,13 @@ if a.mode == "emulate":
     local_stream = np.empty((part.nT, 5), dtype=np.uint32)
     local_stream[:, 0] = 4
     local_stream[:, 1:] = g2l[tets[elems]]
-    sub = ob.OracleScene(nodes.reshape(-1, 3)[l2g].reshape(-1), local_stream.reshape(-1))
+    # the local sub-mesh with the FULL mesh's rest positions (after autoResize), masses and flags
+    full = ob.OracleScene(nodes, idx, DENSITY, AUTO_RESIZE)
+    X0full = full.get_rest()[0]
+    sub = ob.OracleScene(X0full[l2g].astype(np.float32).reshape(-1), local_stream.reshape(-1))
     sub.set_order(np.arange(part.nT, dtype=np.uint32))
     w, flags = part.initial()
+    sub.copy_elements_from(full, elems, rest=X0full[l2g])
     sub.set_state(w=w)
     sub.set_flags(flags)
     st = ob.make_settings(**kw)
@@ -92,8 +106,9 @@ if a.mode == "emulate":
 else:
     torch.cuda.set_device(local_rank)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint,
-                               schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[a.schedule])
+    part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=local_rank, color_hint=hint, partition=PARTITION, density=DENSITY, auto_resize=AUTO_RESIZE,
+                               schedule={"auto": xf.SCHEDULE_AUTO, "dataflow": xf.SCHEDULE_DATAFLOW, "persistent": xf.SCHEDULE_PERSISTENT,
+                                         "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[a.schedule])
     blob = torch.from_numpy(part.ipc_export()).cuda()
     allb = [torch.empty_like(blob) for _ in range(world)]
     dist.all_gather(allb, blob)
@@ -131,7 +146,10 @@ if rank == 0:
             if not (np.array_equal(Xr, Xo[g]) and np.array_equal(Vr, Vo[g]) and np.array_equal(wr, wo[g])):
                 ok = False
                 msg = "rank %d differs: max|dX| = %.3e" % (r, np.abs(Xr - Xo[g]).max())
-    out = {"mode": a.mode, "schedule": a.schedule, "world": world, "tets": int(idx.size // 5), "verts": int(nVg), "ok": ok, "msg": msg,
+    copies = np.zeros(nVg, dtype=np.int64)
+    for g, _, _, _ in gathered:
+        copies[g] += 1
+    out = {"mode": a.mode, "schedule": a.schedule, "partition": a.partition, "max_copies": int(copies.max()), "world": world, "tets": int(idx.size // 5), "verts": int(nVg), "ok": ok, "msg": msg,
            "shared_verts_rank0": int(sum(len(part.halo(c, s, True)) for c in range(part.nColors) for s in range(part.nPeers)))}
     if a.mode == "gpu" and a.time_substeps:
         out["us_per_substep"] = 1e6 * timing / a.time_substeps

@@ -99,6 +99,53 @@ def test_partitioned_emulation_matches_single_scene_oracle(world, extra):
     assert out["shared_verts_rank0"] > 0
 
 
+@pytest.mark.parametrize("world,extra", [(2, []), (3, ["--energy", "4", "--poisson", "0.495"]), (4, ["--dims", "10", "4", "--wonk", "0.3"]),
+                                         (4, ["--mesh", "armadillo", "--energy", "4"])])
+def test_graph_partition_emulation_matches_single_scene_oracle(world, extra):
+    """XF_PARTITION_GRAPH (greedy graph growing): parts with irregular cuts and vertices copied on more than two ranks, on a wonky
+    block and on the reference's Armadillo (irregular valence, generic colouring, autoResize), against the unpartitioned oracle."""
+    if "armadillo" in extra:
+        from oracle import bindings as ob
+        if not ob.have_ref("strict"):
+            pytest.skip("the Armadillo asset lives in the reference (oracle/_ref not built)")
+    out = run_ranks(world, ["--mode", "emulate", "--dims", "8", "3", "--substeps", "6", "--partition", "graph"] + extra, 29651 + world)
+    assert out["ok"], out["msg"]
+    assert out["shared_verts_rank0"] > 0
+    if world >= 4:
+        assert out["max_copies"] >= 3, "the graph partition of this mesh should cut through vertices shared by three parts"
+
+
+def test_graph_partition_plan_is_balanced_and_connected():
+    nodes, idx, hint = xf.GenerateTetBlock(12, 5, wonkiness=0.2)
+    world = 4
+    parts = [xf.GeoPartitionCuda(nodes, idx, world, r, device=-1, color_hint=hint, partition=xf.PARTITION_GRAPH) for r in range(world)]
+    tets = idx.reshape(-1, 5)[:, 1:]
+    sizes = [p.nT for p in parts]
+    assert sum(sizes) == len(tets) and max(sizes) - min(sizes) <= 0.02 * len(tets) + 1
+    owned = np.concatenate([p.local_elements()[0] for p in parts])
+    assert np.array_equal(np.sort(owned), np.arange(len(tets)))
+    for p in parts:  # every part is one connected piece (elements adjacent through a shared vertex)
+        e, _ = p.local_elements()
+        sub = tets[e]
+        comp = np.arange(len(sub))
+        first = {}
+        parent = list(range(len(sub)))
+
+        def find(a):
+            while parent[a] != a:
+                parent[a] = parent[parent[a]]
+                a = parent[a]
+            return a
+        for k, t in enumerate(sub):
+            for v in t:
+                if int(v) in first:
+                    parent[find(k)] = find(first[int(v)])
+                else:
+                    first[int(v)] = k
+        assert len({find(k) for k in range(len(sub))}) == 1
+        assert not p.dataflow_codes()[2] or world <= 2  # more than two copies of some vertex: the flag protocol applies
+
+
 def gpu_count():
     try:
         return xf.device_count()
@@ -115,6 +162,19 @@ def test_partitioned_gpu_matches_oracle(extra):
         pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
     out = run_ranks(2, ["--mode", "gpu", "--dims", "12", "6", "--substeps", "15"] + extra, 29633)
     assert out["ok"], out["msg"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world,extra", [(2, ["--schedule", "auto"]), (4, ["--schedule", "auto", "--dims", "14", "6", "--wonk", "0.3"]),
+                                         (4, ["--schedule", "persistent", "--energy", "4", "--poisson", "0.495"])])
+def test_graph_partitioned_gpu_matches_oracle(world, extra):
+    """XF_PARTITION_GRAPH on the GPUs: vertices with copies on three or four ranks, flag protocol over NVLink, bit-exact."""
+    if gpu_count() < world:
+        pytest.skip("needs at least %d GPUs (run with gpurun --gpus %d)" % (world, world))
+    out = run_ranks(world, ["--mode", "gpu", "--dims", "12", "6", "--substeps", "15", "--partition", "graph"] + extra, 29671 + world)
+    assert out["ok"], out["msg"]
+    if world >= 4:
+        assert out["max_copies"] >= 3
 
 
 @pytest.mark.gpu

@@ -20,6 +20,7 @@ LIB_PATH = os.environ.get("XF_LIB_OVERRIDE") or os.path.join(_HERE, "libxpbd_fem
 
 XF_ABI_VERSION = 2
 XF_OK, XF_ERR_INVALID, XF_ERR_CUDA, XF_ERR_UNSUPPORTED, XF_ERR_NOMEM, XF_ERR_COLORING = 0, -1, -2, -3, -4, -5
+PARTITION_SLABS, PARTITION_GRAPH = 0, 1
 PRECISION_EXACT, PRECISION_FAST = 0, 1
 GROUPING_AUTO, GROUPING_ELEMENTS, GROUPING_CLUSTERS, GROUPING_CHAINS = 0, 1, 2, 3
 SCHEDULE_AUTO, SCHEDULE_LAUNCH_PER_COLOR, SCHEDULE_PERSISTENT, SCHEDULE_BRICKS, SCHEDULE_DATAFLOW = 0, 1, 2, 3, 4
@@ -68,7 +69,7 @@ class CreateParams(C.Structure):
     _fields_ = [
         ("abiVersion", C.c_uint32), ("device", C.c_int32), ("density", C.c_float), ("autoResize", C.c_int32),
         ("precision", C.c_int32), ("schedule", C.c_int32), ("stream", C.c_void_p), ("colorHint", C.c_void_p),
-        ("colorHintCount", C.c_uint32), ("grouping", C.c_uint32), ("_reserved", C.c_uint32 * 4),
+        ("colorHintCount", C.c_uint32), ("grouping", C.c_uint32), ("partition", C.c_uint32), ("_reserved", C.c_uint32 * 3),
     ]
 
 
@@ -648,7 +649,7 @@ class GeoPartitionCuda:
     IPC_BYTES = 128
 
     def __init__(self, nodes, idx_stream, n_ranks, rank, density=1.0, auto_resize=False, device=0, precision=PRECISION_EXACT,
-                 color_hint=None, stream=None, schedule=SCHEDULE_AUTO):
+                 color_hint=None, stream=None, schedule=SCHEDULE_AUTO, partition=0):
         L = lib()
         nodes = np.ascontiguousarray(nodes, dtype=np.float32).reshape(-1)
         idx_stream = np.ascontiguousarray(idx_stream, dtype=np.uint32).reshape(-1)
@@ -660,6 +661,7 @@ class GeoPartitionCuda:
         p.precision = precision
         p.schedule = schedule
         p.stream = stream
+        p.partition = partition
         if color_hint is not None:
             color_hint = np.ascontiguousarray(color_hint, dtype=np.uint32)
             p.colorHint = color_hint.ctypes.data

@@ -647,7 +647,7 @@ int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_
 	std::string err;
 	int rc = PrepareMesh(nodeXYZ, nodeFloatCount, idxStream, idxCount, params->density, params->autoResize != 0, params->colorHint,
 	                     params->colorHintCount, &P->mesh, &err);
-	if (rc == XF_OK) { rc = BuildPartition(P->mesh, nRanks, rank, &P->plan, &err); }
+	if (rc == XF_OK) { rc = BuildPartition(P->mesh, nRanks, rank, &P->plan, &err, params->partition); }
 	if (rc != XF_OK) { delete P; return Fail(rc, err); }
 	if (P->plan.peers.size() > (size_t)kMaxPeers) { delete P; return Fail(XF_ERR_UNSUPPORTED, "a rank may share vertices with at most 16 other ranks"); }
 	memset(&P->dev, 0, sizeof(P->dev));

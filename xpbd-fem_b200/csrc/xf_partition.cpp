@@ -17,7 +17,104 @@
 
 namespace xf {
 
-int BuildPartition(const HostMesh& m, uint32_t nRanks, uint32_t rank, PartPlan* out, std::string* err) {
+namespace {
+
+// XF_PARTITION_GRAPH: greedy graph growing.  Elements are nodes, two elements are adjacent when they share a vertex.  Part q
+// starts from the unassigned element that is farthest (in breadth-first hops) from everything assigned so far - the first one
+// from a peripheral element found by two sweeps - and grows breadth-first until it holds its share of the elements; what a
+// part cannot reach (disconnected leftovers) goes to the part that owns a neighbour, else to the smallest part.  Deterministic:
+// every rank computes the same assignment.
+void GraphGrow(const HostMesh& m, uint32_t nRanks, std::vector<uint8_t>* elemRank) {
+	const uint32_t nT = m.nT, kNone = 0xffu;
+	std::vector<uint32_t> vStart(m.nV + 1, 0), vElems(4 * (size_t)nT);
+	for (size_t k = 0; k < 4 * (size_t)nT; k++) { vStart[m.idx[k] + 1]++; }
+	for (uint32_t v = 0; v < m.nV; v++) { vStart[v + 1] += vStart[v]; }
+	{
+		std::vector<uint32_t> fill(vStart.begin(), vStart.end() - 1);
+		for (uint32_t e = 0; e < nT; e++) { for (int j = 0; j < 4; j++) { vElems[fill[m.idx[4 * (size_t)e + j]]++] = e; } }
+	}
+	std::vector<uint8_t>& owner = *elemRank;
+	owner.assign(nT, (uint8_t)kNone);
+	std::vector<uint32_t> dist(nT), queue;
+	queue.reserve(nT);
+	// breadth-first distances from `sources` over the elements for which `pass(e)` holds; returns the last element reached
+	auto sweep = [&](const std::vector<uint32_t>& sources, bool unassignedOnly) {
+		std::fill(dist.begin(), dist.end(), 0xffffffffu);
+		queue.clear();
+		for (uint32_t s : sources) { dist[s] = 0; queue.push_back(s); }
+		uint32_t last = sources.empty() ? 0u : sources[0];
+		for (size_t h = 0; h < queue.size(); h++) {
+			const uint32_t e = queue[h];
+			if (!unassignedOnly || owner[e] == kNone) { last = e; }
+			for (int j = 0; j < 4; j++) {
+				const uint32_t v = m.idx[4 * (size_t)e + j];
+				for (uint32_t k = vStart[v]; k < vStart[v + 1]; k++) {
+					const uint32_t f = vElems[k];
+					if (dist[f] == 0xffffffffu) { dist[f] = dist[e] + 1; queue.push_back(f); }
+				}
+			}
+		}
+		return last;
+	};
+	uint32_t assigned = 0;
+	std::vector<uint32_t> partSize(nRanks, 0), frontier;
+	for (uint32_t q = 0; q < nRanks; q++) {
+		const uint32_t want = (uint32_t)(((uint64_t)nT * (q + 1)) / nRanks) - assigned;
+		// seed: farthest unassigned element from the assigned ones (q == 0: a peripheral element of the mesh)
+		uint32_t seed = 0;
+		if (q == 0) {
+			seed = sweep({ sweep({ 0u }, false) }, false);
+		} else {
+			std::vector<uint32_t> src;
+			for (uint32_t e = 0; e < nT; e++) { if (owner[e] != kNone) { src.push_back(e); } }
+			seed = sweep(src, true);
+			if (owner[seed] != kNone) { for (uint32_t e = 0; e < nT; e++) { if (owner[e] == kNone) { seed = e; break; } } }
+		}
+		// grow
+		frontier.assign(1, seed);
+		owner[seed] = (uint8_t)q;
+		uint32_t got = 1;
+		for (size_t h = 0; h < frontier.size() && got < want; h++) {
+			const uint32_t e = frontier[h];
+			for (int j = 0; j < 4 && got < want; j++) {
+				const uint32_t v = m.idx[4 * (size_t)e + j];
+				for (uint32_t k = vStart[v]; k < vStart[v + 1] && got < want; k++) {
+					const uint32_t f = vElems[k];
+					if (owner[f] == kNone) { owner[f] = (uint8_t)q; frontier.push_back(f); got++; }
+				}
+			}
+		}
+		partSize[q] = got;
+		assigned += got;
+	}
+	// leftovers (a part ran out of reachable elements): join a neighbour's part, else the smallest part
+	for (bool progress = true; progress && assigned < nT;) {
+		progress = false;
+		for (uint32_t e = 0; e < nT; e++) {
+			if (owner[e] != kNone) { continue; }
+			uint32_t best = kNone;
+			for (int j = 0; j < 4; j++) {
+				const uint32_t v = m.idx[4 * (size_t)e + j];
+				for (uint32_t k = vStart[v]; k < vStart[v + 1]; k++) {
+					const uint32_t o = owner[vElems[k]];
+					if (o != kNone && (best == kNone || partSize[o] < partSize[best])) { best = o; }
+				}
+			}
+			if (best != kNone) { owner[e] = (uint8_t)best; partSize[best]++; assigned++; progress = true; }
+		}
+	}
+	for (uint32_t e = 0; e < nT; e++) {
+		if (owner[e] == kNone) {
+			const uint32_t q = (uint32_t)(std::min_element(partSize.begin(), partSize.end()) - partSize.begin());
+			owner[e] = (uint8_t)q;
+			partSize[q]++;
+		}
+	}
+}
+
+}  // namespace
+
+int BuildPartition(const HostMesh& m, uint32_t nRanks, uint32_t rank, PartPlan* out, std::string* err, uint32_t method) {
 	if (nRanks == 0 || nRanks > 64 || rank >= nRanks) { *err = "nRanks must be 1..64 and rank < nRanks"; return XF_ERR_INVALID; }
 	if (m.nT < nRanks) { *err = "fewer elements than ranks"; return XF_ERR_INVALID; }
 	PartPlan& p = *out;
@@ -36,6 +133,7 @@ int BuildPartition(const HostMesh& m, uint32_t nRanks, uint32_t rank, PartPlan* 
 	std::stable_sort(byX.begin(), byX.end(), [&](uint32_t a, uint32_t b) { return cx[a] < cx[b]; });
 	p.elemRank.assign(m.nT, 0);
 	for (uint32_t k = 0; k < m.nT; k++) { p.elemRank[byX[k]] = (uint8_t)(((uint64_t)k * nRanks) / m.nT); }
+	if (method == XF_PARTITION_GRAPH) { GraphGrow(m, nRanks, &p.elemRank); }
 
 	// 2. which ranks touch each vertex
 	std::vector<uint64_t> mask(m.nV, 0);

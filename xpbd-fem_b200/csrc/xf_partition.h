@@ -28,6 +28,6 @@ struct PartPlan {
 	bool dataflowOk = false;
 };
 
-int BuildPartition(const HostMesh& full, uint32_t nRanks, uint32_t rank, PartPlan* out, std::string* err);
+int BuildPartition(const HostMesh& full, uint32_t nRanks, uint32_t rank, PartPlan* out, std::string* err, uint32_t method = XF_PARTITION_SLABS);
 
 }  // namespace xf
