@@ -25,67 +25,168 @@ def centre_of_mass(X, w):
     return (X * m[:, None]).sum(0) / m.sum()
 
 
-def test_1000_frame_trajectory_exact_and_fast_statistics():
+def record(name, values):
+    """Measured statistics go to gpurun_out/r2_trajectory_stats.json (copied to profiles/ and quoted in DESIGN.md)."""
+    import json, os
+    from __graft_entry__ import ROOT
+    path = os.path.join(ROOT, "gpurun_out", "r2_trajectory_stats.json")
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    try:
+        with open(path) as f:
+            data = json.load(f)
+    except Exception:
+        data = {}
+    data[name] = values
+    with open(path, "w") as f:
+        json.dump(data, f, indent=1)
+
+
+@pytest.mark.parametrize("energy", [xf.Energy_MixedSel, xf.Energy_YeohSkinFast])
+def test_1000_frame_trajectory_exact_and_fast_statistics(energy):
+    """north_star's statistics over a 1000-frame trajectory.  EXACT must reproduce the oracle bit for bit after all 50 000
+    substeps.  FAST (FMA contraction) is judged against the reference's OWN spread: the unmodified reference built with and
+    without FMA contraction (oracle/_ref fast vs strict), same serial order, same frames - the bound is 3x that spread
+    (sampled every 50 frames, maximum over the trajectory), not an absolute number."""
     nodes, idx, hint = xf.GenerateTetBlock(8, 8)
-    kw = dict(energy=xf.Energy_MixedSel, poisson=0.5, gravity=(0.0, -0.4905), lock_left=True)
+    kw = dict(energy=energy, poisson=0.5, gravity=(0.0, -0.4905), lock_left=True)
     st, ost = xf.make_settings(**kw), ob.make_settings(**kw)
     exact = xf.GeoLinear3dCuda(nodes, idx, precision=xf.PRECISION_EXACT, color_hint=hint)
     fast = xf.GeoLinear3dCuda(nodes, idx, precision=xf.PRECISION_FAST, color_hint=hint)
     orc = ob.OracleScene(nodes, idx)
-    orc.set_order(exact.get_order())
+    order = exact.get_order()
+    orc.set_order(order)
+    have_ref = ob.have_ref("fast") and ob.have_ref("strict")
+    refs = []
+    if have_ref:
+        refs = [ob.RefScene.mesh(nodes, idx, kind="strict"), ob.RefScene.mesh(nodes, idx, kind="fast")]
+        for r in refs:
+            r.set_order(order)
+    # the CPU runs (oracle, and the two reference builds sampled like the GPU runs) go on host threads: ctypes drops the GIL
+    from concurrent.futures import ThreadPoolExecutor
+
+    def ref_samples(r):
+        out = []
+        probe = ob.OracleScene(nodes, idx)  # evaluates the energies of the reference's states (xo_energy, checked against xf_stats elsewhere)
+        for _ in range(FRAMES // 50):
+            r.substep(ost, DT, 50 * SUB)
+            X, V, w = r.get_state()
+            probe.set_state(X, V, w)
+            kin, grav, dev, _ = probe.energy(ost)
+            out.append((centre_of_mass(X, w), r.volume(), kin + grav + dev))
+        return out
+    pool = ThreadPoolExecutor(max_workers=3)
+    orc_job = pool.submit(lambda: orc.substep(ost, DT, FRAMES * SUB))
+    ref_jobs = [pool.submit(ref_samples, r) for r in refs]
     vol0 = exact.CalculateVolume()
-    vol_exact, vol_fast, e_exact, e_fast = [], [], [], []
+    bbox = float(np.ptp(exact.get_rest()[0], axis=0).max())
+    series = dict(vol_exact=[], vol_fast=[], e_exact=[], e_fast=[], com_gap=[], vol_gap=[], ref_com_gap=[], ref_vol_gap=[], ref_e_a=[], ref_e_b=[])
     for frame in range(FRAMES):
         exact.Substep(st, DT, SUB)
         fast.Substep(st, DT, SUB)
         if frame % 50 == 49:
-            vol_exact.append(exact.CalculateVolume() / vol0)
-            vol_fast.append(fast.CalculateVolume() / vol0)
             se, sf = exact.stats(st), fast.stats(st)
-            e_exact.append(se["kinetic"] + se["gravitational"] + se["deviatoric"])
-            e_fast.append(sf["kinetic"] + sf["gravitational"] + sf["deviatoric"])
             assert se["nonfinite"] == 0 and sf["nonfinite"] == 0
-    orc.substep(ost, DT, FRAMES * SUB)
+            Xe, _, we = exact.get_state()
+            Xf, _, wf = fast.get_state()
+            ve, vf = exact.CalculateVolume() / vol0, fast.CalculateVolume() / vol0
+            series["vol_exact"].append(ve)
+            series["vol_fast"].append(vf)
+            series["e_exact"].append(se["kinetic"] + se["gravitational"] + se["deviatoric"])
+            series["e_fast"].append(sf["kinetic"] + sf["gravitational"] + sf["deviatoric"])
+            series["com_gap"].append(float(np.abs(centre_of_mass(Xf, wf) - centre_of_mass(Xe, we)).max() / bbox))
+            series["vol_gap"].append(abs(ve - vf))
+    orc_job.result()
+    if have_ref:
+        for (ca, va, ea), (cb, vb, eb) in zip(ref_jobs[0].result(), ref_jobs[1].result()):
+            series["ref_com_gap"].append(float(np.abs(ca - cb).max() / bbox))
+            series["ref_vol_gap"].append(abs(va - vb) / vol0)
+            series["ref_e_a"].append(ea)
+            series["ref_e_b"].append(eb)
+    pool.shutdown()
     Xe, Ve, we = exact.get_state()
     Xo, Vo, wo = orc.get_state()
     # exact: identical after 50 000 substeps
     assert np.array_equal(Xe, Xo) and np.array_equal(Ve, Vo) and np.array_equal(we, wo)
     assert exact.CalculateVolume() == orc.volume()
-    # volume preservation: this swinging cantilever deviates by ~1 % at one XPBD iteration per substep - and the
-    # exact run IS the reference's trajectory (bit-identical above), so the bound is on the reference's own number
-    assert max(abs(v - 1.0) for v in vol_exact) < 2e-2
-    assert max(abs(v - 1.0) for v in vol_fast) < 2e-2
-    # fast vs exact: statistics, against the reference's own fma/no-fma spread when both reference builds are here
-    Xf, Vf, wf = fast.get_state()
-    bbox = (Xo.max(0) - Xo.min(0)).max()
-    com_gap = np.abs(centre_of_mass(Xf, wf) - centre_of_mass(Xo, wo)).max() / bbox
-    vol_gap = max(abs(a - b) for a, b in zip(vol_exact, vol_fast))
-    scale_e = max(abs(e) for e in e_exact)
-    energy_gap = max(abs(a - b) for a, b in zip(e_exact, e_fast)) / scale_e
-    mean_gap = abs(np.mean(e_exact) - np.mean(e_fast)) / scale_e
-    noise_com = noise_vol = 0.0
-    if ob.have_ref("fast") and ob.have_ref("strict"):
-        ra, rb = ob.RefScene.mesh(nodes, idx, kind="strict"), ob.RefScene.mesh(nodes, idx, kind="fast")
-        for r in (ra, rb):
-            r.set_order(exact.get_order())
-            r.substep(ost, DT, 4000)  # the spread saturates within a few thousand substeps at nu = 0.5
-        Xa, _, wa = ra.get_state()
-        Xb, _, wb = rb.get_state()
-        noise_com = np.abs(centre_of_mass(Xa, wa) - centre_of_mass(Xb, wb)).max() / bbox
-        noise_vol = abs(ra.volume() - rb.volume()) / vol0
-    print("fast-vs-exact after %d substeps: com gap %.2e x bbox (reference fma/no-fma spread %.2e), volume-ratio gap %.2e (ref %.2e), "
-          "energy gap: max sample %.2e, mean %.2e of |E|max=%.3e; exact E range over 2nd half %.3e"
-          % (FRAMES * SUB, com_gap, noise_com, vol_gap, noise_vol, energy_gap, mean_gap, scale_e,
-             max(e_exact[len(e_exact) // 2:]) - min(e_exact[len(e_exact) // 2:])))
-    assert com_gap < max(2e-3, 20 * noise_com)      # bounded drift of the mean position
-    assert vol_gap < max(2e-4, 20 * noise_vol)
-    # sample-wise energies of two runs of an oscillating, slightly chaotic system decorrelate in phase; the time
-    # average is the meaningful drift statistic
-    assert mean_gap < 5e-2
-    assert energy_gap < 0.5
-    # energy drift of the exact run itself over the second half of the trajectory (settled cantilever oscillation)
-    half = e_exact[len(e_exact) // 2:]
-    assert (max(half) - min(half)) / scale_e < 0.5
+    if have_ref:  # and the unmodified reference's strict build lands on the same bits
+        assert np.array_equal(refs[0].get_state()[0], Xo)
+    scale_e = max(abs(e) for e in series["e_exact"])
+    stats = dict(
+        substeps=FRAMES * SUB, bbox=bbox,
+        volume_dev_exact_max=max(abs(v - 1.0) for v in series["vol_exact"]), volume_dev_fast_max=max(abs(v - 1.0) for v in series["vol_fast"]),
+        com_gap_max=max(series["com_gap"]), vol_gap_max=max(series["vol_gap"]),
+        ref_com_gap_max=max(series["ref_com_gap"]) if have_ref else None, ref_vol_gap_max=max(series["ref_vol_gap"]) if have_ref else None,
+        energy_mean_gap=abs(np.mean(series["e_exact"]) - np.mean(series["e_fast"])) / scale_e,
+        ref_energy_mean_gap=abs(np.mean(series["ref_e_a"]) - np.mean(series["ref_e_b"])) / scale_e if have_ref else None,
+        ref_energy_sample_gap_max=max(abs(a - b) for a, b in zip(series["ref_e_a"], series["ref_e_b"])) / scale_e if have_ref else None,
+        energy_sample_gap_max=max(abs(a - b) for a, b in zip(series["e_exact"], series["e_fast"])) / scale_e,
+        energy_range_second_half=(max(series["e_exact"][10:]) - min(series["e_exact"][10:])) / scale_e, energy_scale=scale_e)
+    record("box_l_energy_%d" % energy, stats)
+    print(stats)
+    # Measured on B200 (profiles/r2_trajectory_stats.json): this undamped incompressible cantilever is chaotic - the reference's own
+    # two builds drift 3-5e-2 x bbox apart in centre of mass over 1000 frames, the FAST build drifts from EXACT by the same amount
+    # (ratio 1.03-1.13) - so every bound below is a multiple of the reference's own spread on the same frames.
+    # The exact run IS the reference's trajectory (bit-identical above): its volume deviation (4-5e-4) is the reference's number.
+    assert stats["volume_dev_exact_max"] < 1.5e-3
+    assert stats["volume_dev_fast_max"] <= 3.0 * stats["volume_dev_exact_max"]
+    if have_ref:
+        assert stats["com_gap_max"] <= 3.0 * stats["ref_com_gap_max"] + 1e-6, stats
+        assert stats["vol_gap_max"] <= 3.0 * stats["ref_vol_gap_max"] + 1e-7, stats
+        assert stats["energy_sample_gap_max"] <= 3.0 * stats["ref_energy_sample_gap_max"] + 1e-6, stats
+        # time averages of 20 samples of two decorrelated oscillations: within 3x the reference pair's, or 3 sigma of the mean of
+        # 20 independent samples of the reference pair's sample spread
+        assert stats["energy_mean_gap"] <= max(3.0 * stats["ref_energy_mean_gap"], 3.0 * stats["ref_energy_sample_gap_max"] / np.sqrt(20.0)), stats
+    else:  # a box without the reference build: the spreads measured with it (profiles/r2_trajectory_stats.json), times 3
+        assert stats["com_gap_max"] < 0.16 and stats["vol_gap_max"] < 2e-3 and stats["energy_mean_gap"] < 0.15
+    # the settled oscillation neither gains nor loses energy systematically
+    assert stats["energy_range_second_half"] < 0.5
+
+
+def test_100_frames_at_1m_tets_device_statistics_only():
+    """998 250 tets, 100 frames (5000 substeps) with the web default damping on the barrier-free kernel, watched through xf_stats
+    alone (no CPU replay of the trajectory): nothing non-finite, volume held to 1e-3 at every sample.  At the end the state is
+    handed to the CPU oracle once: its energies must agree with xf_stats, and two more (damped) substeps must agree bit for bit.
+    The sampled energies are recorded (profiles/r2_trajectory_stats.json); they are the reference algorithm's own numbers, the
+    oracle in the same serial order reproduces them (tools/damped_diag.py)."""
+    nodes, idx, hint = xf.GenerateTetBlock(55, 55)
+    geo = xf.GeoLinear3dCuda(nodes, idx, color_hint=hint)
+    kw = dict(energy=xf.Energy_MixedSel, poisson=0.5, damping=0.005, rayleigh=xf.Rayleigh_PostAmortized, pbd_damping=0.03)
+    st, ost = xf.make_settings(**kw), ob.make_settings(**kw)
+    st.drag = 0.002
+    xf.frame_constants(st, xf.new_frame_state())
+    for f in ("volumeAndTimeCorrectedPbdDamping", "amortizedVolumeAndTimeCorrectedPbdDamping", "timeCorrectedDrag"):
+        setattr(ost, f, getattr(st, f))
+    s0 = geo.stats(st)
+    vol0 = s0["volume"]
+    samples = []
+    for frame in range(100):
+        geo.Substep(st, DT, SUB)
+        st.tickId += SUB
+        if frame % 10 == 9:
+            s = geo.stats(st)
+            assert s["nonfinite"] == 0
+            samples.append(dict(volume_ratio=s["volume"] / vol0, kinetic=s["kinetic"], released=s0["gravitational"] - s["gravitational"],
+                                deviatoric=s["deviatoric"] - s0["deviatoric"]))
+    assert geo.info()["lastKernel"] == "k_substeps_dataflow_general"
+    record("block_1m_100_frames_damped_mixedsel", samples)
+    print(samples)
+    for q in samples:
+        assert abs(q["volume_ratio"] - 1.0) < 1e-3
+        assert q["released"] > 0.0   # it sags
+    X, V, w = geo.get_state()
+    orc = ob.OracleScene(nodes, idx)
+    orc.set_order(geo.get_order())
+    orc.set_state(X, V, w)
+    kin, grav, dev, _ = orc.energy(ost)
+    s = geo.stats(st)
+    assert abs(kin - s["kinetic"]) <= 1e-9 * abs(kin) and abs(grav - s["gravitational"]) <= 1e-9 * abs(grav) and abs(dev - s["deviatoric"]) <= 1e-6 * abs(dev)
+    ost.tickId = st.tickId
+    geo.Substep(st, DT, 2)
+    orc.substep(ost, DT, 2)
+    Xg, Vg, wg = geo.get_state()
+    Xo, Vo, wo = orc.get_state()
+    assert np.array_equal(Xg, Xo) and np.array_equal(Vg, Vo) and np.array_equal(wg, wo)
+    geo.close()
 
 
 @pytest.fixture(scope="module")
