@@ -169,14 +169,12 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow_general(const Devi
 	const uint32_t stride = 1u + nC * (1u + VP) + (anyDamp ? 1u : 0u);
 	const uint32_t sleepNs = tuning & 0x7fffu, elemSleepNs = tuning >> 16;
 	const bool spare = warpSlot >= sc.maxColorSize;
-	ElemRec rec;
 	bool dead = false;
 	for (uint32_t s = 0; s <= nSubsteps; s++) {
 		const bool closing = s == nSubsteps;
 		if (closing && anyDamp) { break; } // the last substep's post phase already ran, before its damping sweeps
 		const uint32_t stageBase = verBase + s * stride;             // tag of this substep's predict stage
 		const uint32_t prevLast = stageBase - stride + nC * VP;      // + lastCode: last writer of the previous substep's last pass
-		if (!closing && !spare && p.colorStart[0] + warpSlot + lane < p.colorStart[1]) { DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[0] + warpSlot + lane, rec); }
 		// ---- vertex phase at the head of the substep: [post of the previous substep +] predict
 		for (uint32_t i0 = warpSlot; i0 < sc.nV; i0 += gsize) {
 			const uint32_t i = i0 + lane;
@@ -211,22 +209,22 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow_general(const Devi
 			}
 		}
 		if (closing) { break; }
-		// ---- main sweep and volume passes; as in k_substeps_dataflow the record of this thread's element of the NEXT stage is loaded
-		// right after the current one is solved, and the one after next is pulled into L1
+		// ---- main sweep and volume passes.  The element record is loaded where it is used (carrying the next stage's record in
+		// registers across the solve, as k_substeps_dataflow does, cost more in spills here than it hid: 4.17 vs 3.96 ms per 50
+		// damped substeps at 1M tets); the records of the next two stages are pulled into L1 instead.
 		if (!spare) {
 			const uint32_t nStages = nC * (1u + VP);
 			for (uint32_t t = 0; t < nStages; t++) {
 				const uint32_t q = t / nC, c = t - q * nC;
 				const uint32_t passBase = stageBase + nC * q; // + 1 + colour = the tag an element of this pass writes
 				const uint32_t end = p.colorStart[c + 1];
-				bool firstChunk = true;
-				for (uint32_t e0 = p.colorStart[c] + warpSlot; e0 < end; e0 += gsize, firstChunk = false) {
+				for (uint32_t e0 = p.colorStart[c] + warpSlot; e0 < end; e0 += gsize) {
 					const bool has = e0 + lane < end && !dead;
 					const unsigned mask = __ballot_sync(0xffffffffu, has);
 					if (!has) { continue; }
-					ElemRec use = rec;
-					if (!firstChunk) { DataflowLoad<ENERGY, EXACT>(sc, e0 + lane, use); }
-					const uint32_t raw[4] = { use.idx.x, use.idx.y, use.idx.z, use.idx.w };
+					ElemRec rec;
+					DataflowLoad<ENERGY, EXACT>(sc, e0 + lane, rec);
+					const uint32_t raw[4] = { rec.idx.x, rec.idx.y, rec.idx.z, rec.idx.w };
 					uint32_t vid[4], expectTag[4];
 #pragma unroll
 					for (int n = 0; n < 4; n++) {
@@ -238,17 +236,15 @@ __global__ void __launch_bounds__(256, 2) k_substeps_dataflow_general(const Devi
 					}
 					const uint32_t newTag = (passBase + 1u + c) << 8;
 					if (q == 0) {
-						dead = !GeneralElement<0, ENERGY, SIMUL, EXACT>(sc, p, use, mask, vid, expectTag, newTag, elemSleepNs);
+						dead = !GeneralElement<0, ENERGY, SIMUL, EXACT>(sc, p, rec, mask, vid, expectTag, newTag, elemSleepNs);
 					} else {
-						dead = !GeneralElement<1, ENERGY, SIMUL, EXACT>(sc, p, use, mask, vid, expectTag, newTag, elemSleepNs);
+						dead = !GeneralElement<1, ENERGY, SIMUL, EXACT>(sc, p, rec, mask, vid, expectTag, newTag, elemSleepNs);
 					}
 				}
-				const uint32_t c1 = c + 1u < nC ? c + 1u : 0u; // next stage's colour (the last stage preloads for nobody)
-				if (t + 1u < nStages && p.colorStart[c1] + warpSlot + lane < p.colorStart[c1 + 1]) {
-					DataflowLoad<ENERGY, EXACT>(sc, p.colorStart[c1] + warpSlot + lane, rec);
+				for (uint32_t ahead = 1; ahead <= 2u; ahead++) { // wraps into the next pass / substep
+					const uint32_t ca = (c + ahead) % nC;
+					if (p.colorStart[ca] + warpSlot + lane < p.colorStart[ca + 1]) { DataflowPrefetch<ENERGY, EXACT>(sc, p.colorStart[ca] + warpSlot + lane); }
 				}
-				const uint32_t c2 = c1 + 1u < nC ? c1 + 1u : 0u; // wraps into the next pass / substep
-				if (p.colorStart[c2] + warpSlot + lane < p.colorStart[c2 + 1]) { DataflowPrefetch<ENERGY, EXACT>(sc, p.colorStart[c2] + warpSlot + lane); }
 			}
 		}
 		if (!anyDamp) { continue; }

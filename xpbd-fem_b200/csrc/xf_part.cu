@@ -51,6 +51,9 @@ struct PartDevice {
 	const uint32_t* sharedList; // local ids of the shared vertices
 	const uint32_t* privList;   // local ids of the others
 	uint32_t nSharedList, nPrivList, nIfaceWarps;
+	// barrier-free schedule: 1 = a system-scope fence between the peer store and the local store of a shared vertex (the hand-off
+	// to a same-rank successor is then a release/acquire chain by construction); 0 = program order of two relaxed stores only
+	uint32_t releaseStores;
 };
 
 __device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
@@ -301,10 +304,17 @@ struct VersionedMirrorStore {
 	GlobalStore base;
 	uint32_t vid[4];
 	VertexRec* remote[4]; // the peer's copy of corner n, or nullptr
+	bool release;         // fence between the peer store and the local store (PartDevice::releaseStores)
 	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return LoadVertexSys(base.Xw, i); }
 	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const {
 		VertexRec* r = i == vid[0] ? remote[0] : (i == vid[1] ? remote[1] : (i == vid[2] ? remote[2] : remote[3]));
-		if (r) { StoreVertexSys(r, 0, v); }
+		if (r) {
+			StoreVertexSys(r, 0, v);
+			// With the fence the peer store is PERFORMED before the local record can be seen: a same-rank successor that reads the
+			// local record and then stores to the same peer address is ordered after us by the memory model (fence + relaxed store
+			// = release; its poll + the fence it issues before ITS peer store = acquire), not just by the order the stores left.
+			if (release) { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+		}
 		StoreVertexSys(base.Xw, i, v);
 	}
 	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { base.LoadO(i, o); }
@@ -323,6 +333,7 @@ __device__ __forceinline__ bool PartDataflowElement(const PartDevice& pd, const 
 	bool needAck[4];
 	VersionedMirrorStore vs;
 	vs.base = StoreOf(pd.local);
+	vs.release = pd.releaseStores != 0;
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
 		vid[n] = raw[n] & 0x00ffffffu;
@@ -609,6 +620,14 @@ int UploadPart(xf_partition* P) {
 		// one warp per interface chunk of the largest colour, and enough of them for the shared vertices' phase
 		P->dev.nIfaceWarps = pl.peers.empty() ? 0u : std::max((maxIface + 31u) / 32u, ((uint32_t)sharedList.size() + 63u) / 64u);
 		if (const char* env = getenv("XF_PART_IFACE_WARPS")) { P->dev.nIfaceWarps = (uint32_t)atoi(env); }
+		// Measured on 4 x B200 (profiles/r2_part_release_ab_4gpu.log): the fence BREAKS the schedule - every mesh stalls (reported, never
+		// wrong).  While this rank waits in the fence, the peer's successor has already seen our record in ITS copy, solved, and
+		// stored its newer record into OUR copy - and our delayed local store then overwrites it.  The order "peer store, then the
+		// local store a few cycles later" is what keeps both hazards closed (a same-rank successor cannot overtake a peer store issued
+		// >= one L2 round trip + one solve earlier; the peer's answer needs two NVLink flights + a solve, the local store a few cycles):
+		// a property of the timing, not of the memory model, and fail-stop when violated.  Off by default; the knob documents it.
+		P->dev.releaseStores = 0;
+		if (const char* env = getenv("XF_PART_RELEASE")) { P->dev.releaseStores = (uint32_t)atoi(env); }
 		if (!sharedList.empty()) { P->dev.nIfaceWarps = std::max(P->dev.nIfaceWarps, 1u); } // somebody must carry the interface
 		std::vector<ElemRecA> ad = pk.a;
 		for (size_t k = 0; k < ad.size(); k++) {
@@ -666,7 +685,10 @@ int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_
 		// back-to-back launches overlap it slightly better.  AUTO therefore means one launch per phase here.
 		// The barrier-free schedule (versioned records mirrored by peer stores) removes that chain from the element path.
 		if (P->schedule == XF_SCHEDULE_AUTO || P->schedule == XF_SCHEDULE_BRICKS) {
-			P->schedule = (P->plan.dataflowOk && prop.cooperativeLaunch) ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_LAUNCH_PER_COLOR;
+			// graph partitions: measured stalls of the barrier-free schedule at 8M tets on 4 GPUs (irregular interfaces under load,
+			// profiles/r2_part_release_ab_4gpu.log) - AUTO keeps them on the flag protocol, which is ordered by construction
+			const bool slabs = params->partition == XF_PARTITION_SLABS;
+			P->schedule = (P->plan.dataflowOk && prop.cooperativeLaunch && slabs) ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_LAUNCH_PER_COLOR;
 		}
 		if (P->schedule == XF_SCHEDULE_DATAFLOW && !P->plan.dataflowOk) {
 			delete P;
