@@ -326,7 +326,8 @@ int xf_batch_get_info(const xf_batch* batch, uint32_t* groupThreads, uint32_t* b
  * xf_part_ipc_export blob to all ranks once (torch.distributed / MPI / files) and hand them to
  * xf_part_ipc_connect.  All ranks must then issue the same xf_part_substep calls.  Results equal the
  * single-GPU schedule bit for bit.  device < 0 creates a host-only plan (no stepping) whose halo lists can be
- * inspected; damping sweeps and volume passes are not implemented on this path (XF_ERR_UNSUPPORTED). */
+ * inspected.  Calls with damping (in-constraint or post-solve sweeps) or volume passes run on the flag protocol, one launch per
+ * phase, with the velocities of shared vertices mirrored like the positions; the plain sweep on the schedule chosen at creation. */
 typedef struct xf_partition xf_partition;
 #define XF_IPC_BYTES 128
 int xf_part_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream,

@@ -28,6 +28,10 @@ ap.add_argument("--check", type=int, default=1)
 ap.add_argument("--time-substeps", type=int, default=0)
 ap.add_argument("--schedule", choices=["auto", "dataflow", "persistent", "per_color"], default="dataflow")
 ap.add_argument("--partition", choices=["slabs", "graph"], default="slabs")
+ap.add_argument("--damping", type=float, default=0.0, help="Rayleigh damping (with --rayleigh) + PBD damping 0.03: gpu mode only")
+ap.add_argument("--rayleigh", type=int, default=3)
+ap.add_argument("--volume-passes", type=int, default=0)
+ap.add_argument("--mix", action="store_true", help="plain calls before and after the damped ones: the two cross-GPU protocols hand over to each other")
 ap.add_argument("--mesh", choices=["block", "armadillo"], default="block", help="armadillo: the reference's asset (needs oracle/_ref)")
 a = ap.parse_args()
 xf = load_package()
@@ -44,18 +48,48 @@ else:
     hint = None if (a.no_hint or a.pattern != 0) else hint
 PARTITION = {"slabs": xf.PARTITION_SLABS, "graph": xf.PARTITION_GRAPH}[a.partition]
 DENSITY = 2.0 if AUTO_RESIZE else 1.0
-kw = dict(energy=a.energy, simultaneous=not a.serial, poisson=a.poisson)
+kw = dict(energy=a.energy, simultaneous=not a.serial, poisson=a.poisson, volume_passes=a.volume_passes)
+if a.damping > 0.0:
+    kw.update(damping=a.damping, rayleigh=a.rayleigh, pbd_damping=0.03, drag_tc=0.0007)
+GENERAL = a.damping > 0.0 or a.volume_passes > 0
+
+
+def with_constants(st):
+    if a.damping > 0.0:
+        st.volumeAndTimeCorrectedPbdDamping = 1e-6
+        st.amortizedVolumeAndTimeCorrectedPbdDamping = 7e-6
+    return st
+
+
+
+PLAIN_KW = dict(energy=a.energy, simultaneous=not a.serial, poisson=a.poisson)
+# the calls of a run: (settings keywords, substeps); --mix wraps the damped calls in plain ones
+CALLS = [(kw, 1), (kw, a.substeps - 1)]
+if a.mix:
+    CALLS = [(PLAIN_KW, 2)] + CALLS + [(PLAIN_KW, 3), (kw, 2)]
+
+
+def run_calls(scene, make_settings, step):
+    tick = 0
+    for k, n in CALLS:
+        st = make_settings(**k)
+        if k is kw:
+            with_constants(st)
+        st.tickId = tick
+        step(scene, st, n)
+        tick += n
 
 
 def reference_state(order, n):
     from oracle import bindings as ob
     o = ob.OracleScene(nodes, idx, DENSITY, AUTO_RESIZE)
     o.set_order(order)
-    o.substep(ob.make_settings(**kw), DT, n)
+    run_calls(o, ob.make_settings, lambda sc, st, k: sc.substep(st, DT, k))
     return o.get_state()
 
 
 if a.mode == "emulate":
+    assert not GENERAL, "the emulation covers the main sweep; damping / volume passes are checked on the GPUs"
     from oracle import bindings as ob
     dist.init_process_group("gloo")
     part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=-1, color_hint=hint, partition=PARTITION, density=DENSITY, auto_resize=AUTO_RESIZE)
@@ -114,9 +148,8 @@ else:
     dist.all_gather(allb, blob)
     part.ipc_connect(torch.stack(allb).cpu().numpy())
     dist.barrier()
-    st = xf.make_settings(**kw)
-    for n in (1, a.substeps - 1):
-        part.Substep(st, DT, n)
+    st = with_constants(xf.make_settings(**kw))
+    run_calls(part, xf.make_settings, lambda sc, s_, k: sc.Substep(s_, DT, k))
     X, V, ww = part.get_state()
     l2g = part.local_verts()
     order = part.get_order()

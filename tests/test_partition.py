@@ -178,6 +178,23 @@ def test_graph_partitioned_gpu_matches_oracle(world, extra):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("extra", [["--damping", "0.005", "--rayleigh", "3"], ["--damping", "0.005", "--rayleigh", "2", "--energy", "4"],
+                                   ["--damping", "0.004", "--rayleigh", "0", "--energy", "7", "--poisson", "0.495"],
+                                   ["--damping", "0.004", "--rayleigh", "1", "--serial", "--energy", "5", "--poisson", "0.495"],
+                                   ["--volume-passes", "2", "--energy", "4"],
+                                   ["--damping", "0.005", "--rayleigh", "3", "--volume-passes", "1", "--mix"],
+                                   ["--damping", "0.005", "--rayleigh", "3", "--mix", "--schedule", "per_color", "--partition", "graph"]])
+def test_partitioned_damping_and_volume_passes_gpu_match_oracle(extra):
+    """Damping (post-solve sweeps with amortised slices, PBD damping, in-constraint Paper / Limit) and volume passes on a mesh split
+    over two GPUs: flag protocol with mirrored velocities, against the unpartitioned oracle, bit for bit; --mix alternates plain calls
+    (barrier-free cross-GPU kernel) and damped calls (flag protocol) on the same partition."""
+    if gpu_count() < 2:
+        pytest.skip("needs at least 2 GPUs (run with gpurun --gpus 2)")
+    out = run_ranks(2, ["--mode", "gpu", "--dims", "12", "6", "--substeps", "19"] + extra, 29643)
+    assert out["ok"], out["msg"]
+
+
+@pytest.mark.gpu
 def test_partition_single_rank_gpu():
     """nRanks = 1 degenerates to the single-GPU schedule (no peers): still bit-exact."""
     from oracle import bindings as ob

@@ -32,6 +32,7 @@ struct PartDevice {
 	uint32_t nPeers;
 	uint32_t myRank;
 	VertexRec* peerXw[kMaxPeers]; // peers' vertex arrays (IPC-mapped)
+	double4* peerV[kMaxPeers];    // peers' velocity arrays (same IPC mapping: V follows Xw in one allocation)
 	unsigned long long* peerFlags[kMaxPeers]; // peers' flag arrays, indexed by sender rank
 	unsigned long long* myFlags;  // indexed by sender rank
 	uint32_t peerRank[kMaxPeers];
@@ -102,26 +103,52 @@ struct MirroredStore {
 	}
 	__device__ __forceinline__ void LoadO(uint32_t i, double* o) const { base.LoadO(i, o); }
 	__device__ __forceinline__ void LoadV(uint32_t i, double* o) const { base.LoadV(i, o); }
-	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const { base.StoreV(i, v); }
+	// damping sweeps: velocities of shared vertices are mirrored like positions
+	__device__ __forceinline__ void StoreV(uint32_t i, const double* v) const {
+		base.StoreV(i, v);
+		const uint32_t b = __ldg(pd->shareStart + i), e = __ldg(pd->shareStart + i + 1);
+		for (uint32_t k = b; k < e; k++) { StoreD3(pd->peerV[__ldg(pd->shareSlot + k)], __ldg(pd->shareRemoteIdx + k), v); }
+	}
 };
 
-template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
-__global__ void __launch_bounds__(256) k_part_sweep(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, uint32_t begin,
-                                                    uint32_t ifaceEnd, uint32_t end, unsigned long long epoch) {
+// KIND 0: main constraint solve   1: volume-only pass   2: Rayleigh damp (V)   3: PBD damp (V)   (as in xf_kernels.cu)
+template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED, typename VS>
+__device__ __forceinline__ void PartSweepOne(const VS& vs, const DeviceScene& sc, const SubstepParams& p, uint32_t e) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
+	ElemRec rec;
+	if (KIND == 3) {
+		rec.idx = LoadElementIdx(sc, e);
+		PbdDampElement<EXACT>(vs, p, __ldg(sc.eArea + e), rec.idx);
+		return;
+	}
+	LoadElement<(KIND != 1) && kPrefactored, EXACT>(sc, e, rec);
+	if (KIND == 0) { SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec); }
+	if (KIND == 1) { SolveVolumeOnly<EXACT>(vs, p, rec); }
+	if (KIND == 2) { DampElement<ENERGY, SIMUL, EXACT>(vs, p, rec); }
+}
+
+// One phase of the flag protocol: the rank's elements [begin, end) of one colour (interface elements first, up to ifaceEnd).
+// Damping sweeps (KIND >= 2) act on the elements whose GLOBAL serial position lies in [lo, hi) (amortised slices, Geo.cpp:794-797).
+template <int KIND, int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
+__global__ void __launch_bounds__(256) k_part_sweep(const __grid_constant__ PartDevice pd, const __grid_constant__ SubstepParams p, uint32_t begin,
+                                                    uint32_t ifaceEnd, uint32_t end, uint32_t lo, uint32_t hi, unsigned long long epoch) {
 	PhaseWait(pd, epoch);
 	const uint32_t e = begin + blockIdx.x * blockDim.x + threadIdx.x;
-	if (e < end) {
-		ElemRec rec;
-		LoadElement<kPrefactored, EXACT>(pd.local, e, rec);
+	if (e < end && (KIND < 2 || InSlice(pd.local, e, lo, hi))) {
 		if (e < ifaceEnd) {
 			const MirroredStore vs{ StoreOf(pd.local), &pd };
-			SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec);
+			PartSweepOne<KIND, ENERGY, SIMUL, EXACT, DAMPED>(vs, pd.local, p, e);
 		} else {
 			const GlobalStore vs = StoreOf(pd.local);
-			SolveElement<ENERGY, SIMUL, EXACT, DAMPED>(vs, p, rec);
+			PartSweepOne<KIND, ENERGY, SIMUL, EXACT, DAMPED>(vs, pd.local, p, e);
 		}
 	}
+	PhaseSignal(pd, epoch);
+}
+
+// An empty phase: orders this rank's earlier launches (a barrier-free launch of the previous call) before the peers' next phase.
+__global__ void __launch_bounds__(32) k_part_sync_phase(const __grid_constant__ PartDevice pd, unsigned long long epoch) {
+	PhaseWait(pd, epoch);
 	PhaseSignal(pd, epoch);
 }
 
@@ -490,24 +517,58 @@ struct PartPersistentRunner {
 
 template <int ENERGY, bool SIMUL, bool EXACT, bool DAMPED>
 struct PartRunner {
+	// `globalColorStart`: colour ranges of the FULL mesh's serial order (identical on every rank): a damping sweep visits the colours
+	// that meet the slice, and every rank must run the same sequence of phases.
 	static cudaError_t Run(const PartDevice& pd, const SubstepParams& p, const std::vector<uint32_t>& colorStart, const std::vector<uint32_t>& ifaceEnd,
-	                       uint32_t nSubsteps, unsigned long long* epoch, cudaStream_t st, uint64_t* launches) {
-		if (DAMPED) { return cudaErrorNotSupported; }
+	                       const std::vector<uint32_t>& globalColorStart, uint32_t nTGlobal, uint32_t nSubsteps, unsigned long long* epoch,
+	                       cudaStream_t st, uint64_t* launches) {
 		const uint32_t nV = pd.local.nV;
 		const dim3 vgrid((nV + 255) / 256);
 		const uint32_t nC = (uint32_t)colorStart.size() - 1;
+		const bool anyDamp = p.doDamp || p.doPbdDamp;
+		auto blocksOf = [&](uint32_t c) { return dim3(std::max<uint32_t>(1u, (colorStart[c + 1] - colorStart[c] + 255) / 256)); }; // an empty colour still takes part
+		k_part_sync_phase<<<1, 32, 0, st>>>(pd, ++*epoch);
+		++*launches;
 		for (uint32_t s = 0; s < nSubsteps; s++) {
-			k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, s > 0 ? 1 : 0, 1, ++*epoch);
+			k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, (s > 0 && !anyDamp) ? 1 : 0, 1, ++*epoch);
 			++*launches;
 			for (uint32_t c = 0; c < nC; c++) {
-				const uint32_t b = colorStart[c], e = colorStart[c + 1];
-				const uint32_t blocks = std::max<uint32_t>(1u, (e - b + 255) / 256); // an empty colour still takes part in the protocol
-				k_part_sweep<ENERGY, SIMUL, EXACT, false><<<dim3(blocks), 256, 0, st>>>(pd, p, b, ifaceEnd[c], e, ++*epoch);
+				k_part_sweep<0, ENERGY, SIMUL, EXACT, DAMPED><<<blocksOf(c), 256, 0, st>>>(pd, p, colorStart[c], ifaceEnd[c], colorStart[c + 1], 0, 0, ++*epoch);
 				++*launches;
 			}
+			for (uint32_t pass = 0; pass < p.volumePasses; pass++) {
+				for (uint32_t c = 0; c < nC; c++) {
+					k_part_sweep<1, ENERGY, SIMUL, EXACT, false><<<blocksOf(c), 256, 0, st>>>(pd, p, colorStart[c], ifaceEnd[c], colorStart[c + 1], 0, 0, ++*epoch);
+					++*launches;
+				}
+			}
+			if (anyDamp) {
+				k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, 1, 0, ++*epoch);
+				++*launches;
+				uint32_t lo = 0, hi = nTGlobal;
+				if (p.rayleigh == XF_RAYLEIGH_POST_AMORTIZED) { // Geo.cpp:794-797
+					const uint32_t k = (p.tickId + s) % XF_AMORTIZATION_PERIOD;
+					lo = (uint32_t)(((uint64_t)nTGlobal * k) / XF_AMORTIZATION_PERIOD);
+					hi = (uint32_t)(((uint64_t)nTGlobal * (k + 1)) / XF_AMORTIZATION_PERIOD);
+				}
+				for (int sweep = 0; sweep < 2; sweep++) {
+					if (sweep == 0 ? !p.doDamp : !p.doPbdDamp) { continue; }
+					for (uint32_t c = 0; c < nC; c++) {
+						if (!(globalColorStart[c] < hi && globalColorStart[c + 1] > lo)) { continue; } // the same verdict on every rank
+						if (sweep == 0) {
+							k_part_sweep<2, ENERGY, SIMUL, EXACT, false><<<blocksOf(c), 256, 0, st>>>(pd, p, colorStart[c], ifaceEnd[c], colorStart[c + 1], lo, hi, ++*epoch);
+						} else {
+							k_part_sweep<3, ENERGY, SIMUL, EXACT, false><<<blocksOf(c), 256, 0, st>>>(pd, p, colorStart[c], ifaceEnd[c], colorStart[c + 1], lo, hi, ++*epoch);
+						}
+						++*launches;
+					}
+				}
+			}
 		}
-		k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, 1, 0, ++*epoch);
-		++*launches;
+		if (!anyDamp) {
+			k_part_vertex_phase<EXACT><<<vgrid, 256, 0, st>>>(pd, p, 1, 0, ++*epoch);
+			++*launches;
+		}
 		return cudaGetLastError();
 	}
 };
@@ -588,13 +649,23 @@ int UploadPart(xf_partition* P) {
 	for (size_t s = 0; s < pl.peers.size(); s++) { slotOfRank[pl.peers[s]] = (uint32_t)s; }
 	std::vector<uint32_t> shareSlot(pl.sharePeerRank.size());
 	for (size_t k = 0; k < shareSlot.size(); k++) { shareSlot[k] = slotOfRank[pl.sharePeerRank[k]]; }
-	XFP_CUDA(UploadVecP(&d.Xw, xw));
+	// positions and velocities in ONE allocation (V follows Xw): one IPC handle gives a peer both arrays
+	XFP_CUDA(cudaMalloc((void**)&d.Xw, sizeof(VertexRec) * 2 * std::max(nV, 1u)));
+	XFP_CUDA(cudaMemcpy(d.Xw, xw.data(), sizeof(VertexRec) * nV, cudaMemcpyHostToDevice));
+	d.V = reinterpret_cast<double4*>(d.Xw + std::max(nV, 1u));
+	XFP_CUDA(cudaMemset(d.V, 0, sizeof(double4) * std::max(nV, 1u)));
 	XFP_CUDA(UploadVecP(&d.O, x0));
 	XFP_CUDA(UploadVecP(&d.X0, x0));
-	XFP_CUDA(UploadVecP(&d.V, zero));
 	XFP_CUDA(UploadVecP(&d.eA, pk.a));
 	XFP_CUDA(UploadVecP(&d.eB, pk.b));
 	XFP_CUDA(UploadVecP(&d.eC, pk.c));
+	XFP_CUDA(UploadVecP(&d.eArea, pk.area));
+	{ // global serial position of every local element: the damping slices are ranges of the FULL mesh's serial order
+		std::vector<uint32_t> serialPos(m.nT), canon(nT);
+		for (uint32_t k = 0; k < m.nT; k++) { serialPos[m.order[k]] = k; }
+		for (uint32_t k = 0; k < nT; k++) { canon[k] = serialPos[pl.elems[k]]; }
+		XFP_CUDA(UploadVecP(&d.canonPos, canon));
+	}
 	XFP_CUDA(UploadVecP(&P->dShareStart, pl.shareStart));
 	XFP_CUDA(UploadVecP(&P->dShareSlot, shareSlot));
 	XFP_CUDA(UploadVecP(&P->dShareRemote, pl.shareRemoteIdx));
@@ -605,6 +676,11 @@ int UploadPart(xf_partition* P) {
 	const size_t flagBytes = sizeof(unsigned long long) * 64 + sizeof(uint32_t) * std::max(nV, 1u);
 	XFP_CUDA(cudaMalloc((void**)&P->dev.myFlags, flagBytes));
 	XFP_CUDA(cudaMemset(P->dev.myFlags, 0, flagBytes));
+	{ // slot 63 (no rank writes it: nRanks <= 63 flag slots are indexed by sender rank): this rank's local vertex count, so that a
+	  // peer can find V behind Xw in the mapped allocation
+		const unsigned long long nv = std::max(nV, 1u);
+		XFP_CUDA(cudaMemcpy(P->dev.myFlags + 63, &nv, sizeof(nv), cudaMemcpyHostToDevice));
+	}
 	P->dev.myAck = reinterpret_cast<uint32_t*>(P->dev.myFlags + 64);
 	if (pl.dataflowOk) {
 		std::vector<uint32_t> sharedList, privList;
@@ -716,7 +792,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eAd, d.lastCode, P->dSharedList, P->dPrivList, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.X0, d.eA, d.eB, d.eC, d.eArea, d.canonPos, d.eAd, d.lastCode, P->dSharedList, P->dPrivList, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
@@ -815,6 +891,9 @@ int xf_part_ipc_connect(xf_partition* P, const void* allRanks) {
 		P->openedPeers.push_back(fl);
 		P->dev.peerXw[s] = (VertexRec*)xw;
 		P->dev.peerFlags[s] = (unsigned long long*)fl;
+		unsigned long long peerNV = 0; // the peer's local vertex count (flag slot 63): its V array follows its Xw array
+		XFP_CUDA(cudaMemcpy(&peerNV, (unsigned long long*)fl + 63, sizeof(peerNV), cudaMemcpyDeviceToHost));
+		P->dev.peerV[s] = reinterpret_cast<double4*>((VertexRec*)xw + peerNV);
 		P->dev.peerAck[s] = reinterpret_cast<uint32_t*>((unsigned long long*)fl + 64);
 	}
 	P->connected = true;
@@ -839,14 +918,19 @@ int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n
 	std::string err;
 	int rc = FillSubstepParams(st, nullptr, dt, P->mesh, &p, &err);
 	if (rc != XF_OK) { return Fail(rc, err); }
-	if ((p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST) || p.doDamp || p.doPbdDamp || p.volumePasses) {
-		return Fail(XF_ERR_UNSUPPORTED, "the partitioned path implements the undamped main sweep only (damping / volume passes: single-GPU scenes)");
-	}
+	// damping (in-constraint or sweeps) and volume passes run on the flag protocol, whatever the schedule of the plain sweep:
+	// one launch per phase, velocities of shared vertices mirrored like positions
+	const bool inConstraint = p.damping > 0.0f && p.rayleigh < XF_RAYLEIGH_POST;
+	const bool general = inConstraint || p.doDamp || p.doPbdDamp || p.volumePasses;
+	if (P->plan.nRanks > 63) { return Fail(XF_ERR_UNSUPPORTED, "at most 63 ranks"); }
 	p.groundOn = P->groundOn;
 	p.groundY = P->groundY;
 	p.groundKeep = 1.0f - P->groundFriction;
 	p.handleCount = 0;
-	if (P->schedule == XF_SCHEDULE_DATAFLOW) {
+	if (general) {
+		XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, inConstraint, P->dev, p, P->plan.colorStart,
+		                                    P->plan.ifaceEnd, P->mesh.colorStart, P->mesh.nT, n, &P->epoch, P->stream, &P->launches));
+	} else if (P->schedule == XF_SCHEDULE_DATAFLOW) {
 		const uint32_t stride = P->dev.nColors + 1u;
 		const uint32_t maxPerLaunch = (0x00ffffffu - 2u) / stride;
 		for (uint32_t done = 0; done < n;) {
@@ -861,7 +945,7 @@ int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n
 		                                              P->smCount, P->stream, &P->launches));
 	} else {
 		XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, false, P->dev, p, P->plan.colorStart,
-		                                    P->plan.ifaceEnd, n, &P->epoch, P->stream, &P->launches));
+		                                    P->plan.ifaceEnd, P->mesh.colorStart, P->mesh.nT, n, &P->epoch, P->stream, &P->launches));
 	}
 	return XF_OK;
 }
