@@ -448,6 +448,12 @@ class OracleScene:
     def phase_sweep(self, settings, dt, begin, end):
         self.lib.xo_phase_sweep(self.h, C.byref(settings), dt, begin, end)
 
+    def phase_elems(self, settings, dt, kind, elems):
+        """Elements `elems` (scene element indices, in that order) of one sweep: 0 main, 1 volume pass, 2 Rayleigh damp, 3 PBD damp."""
+        elems = np.ascontiguousarray(elems, dtype=np.uint32)
+        self.lib.xo_phase_elems.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_void_p, C.c_uint32]
+        self.lib.xo_phase_elems(self.h, C.byref(settings), dt, int(kind), _vp(elems), elems.size)
+
     def phase_post(self, settings, dt, manip=None):
         self.lib.xo_phase_post(self.h, C.byref(settings), C.byref(manip) if manip is not None else None, dt)
 

@@ -836,6 +836,27 @@ void xo_phase_sweep(xo_scene* s, const xo_settings* st, float dt, uint32_t begin
 	for (uint32_t i = begin; i < end && i < s->nT; i++) { solve_element_mixed(energy, 0, dt, s->X, s->O, NULL, s->w, &s->t[s->tOrder[i]], st); }
 }
 
+/* An explicit list of elements (indices into the scene's tets, in the given order) of one sweep, for emulating a partitioned run:
+ * kind 0 = main solve (Geo.cpp:777), 1 = volume-only pass (Geo.cpp:779-782), 2 = Rayleigh damp, 3 = PBD damp (Geo.cpp:790-811, with
+ * the amortised settings of Geo.cpp:346-355 when the Rayleigh type is PostAmortized). */
+void xo_phase_elems(xo_scene* s, const xo_settings* stIn, float dt, int kind, const uint32_t* elems, uint32_t count) {
+	xo_settings st = *stIn;
+	uint32_t energy = (st.flags >> XO_ENERGY_BIT) & XO_ENERGY_MASK;
+	if (!energy_supported(energy)) { energy = EN_MIXED_SEL; }
+	uint32_t rayleighType = (st.flags >> XO_RAYLEIGH_BIT) & XO_RAYLEIGH_MASK;
+	if (kind >= 2 && rayleighType == RAY_POST_AMORTIZED) {
+		st.damping *= (float)XO_AMORTIZATION_PERIOD;
+		st.volumeAndTimeCorrectedPbdDamping = stIn->amortizedVolumeAndTimeCorrectedPbdDamping;
+	}
+	for (uint32_t k = 0; k < count; k++) {
+		const xo_tet* t = &s->t[elems[k]];
+		if (kind == 0) { solve_element_mixed(energy, 0, dt, s->X, s->O, NULL, s->w, t, &st); }
+		if (kind == 1) { solve_volume_only(dt, s->X, s->O, s->w, t, &st); }
+		if (kind == 2 && rayleighType >= RAY_POST && st.damping > 0.0f) { solve_element_mixed(energy, 1, dt, s->X, NULL, s->V, s->w, t, &st); }
+		if (kind == 3 && st.pbdDamping > 0.0f) { pbd_damp(s->X, s->V, s->w, t->i, fminf(1.0f, st.volumeAndTimeCorrectedPbdDamping / t->surfaceArea)); }
+	}
+}
+
 /* ground (x1) -> locks -> manipulator -> handles (x2) -> velocity update, Geo.cpp:318-344 */
 void xo_phase_post(xo_scene* s, const xo_settings* stp, const xo_manipulator* manip, float dt) {
 	const xo_settings st = *stp;

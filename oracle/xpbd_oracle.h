@@ -63,6 +63,7 @@ void xo_substep(xo_scene* s, const xo_settings* settings, const xo_manipulator* 
  * partitioned multi-rank run on CPU. */
 void xo_phase_predict(xo_scene* s, const xo_settings* settings, float dt);
 void xo_phase_sweep(xo_scene* s, const xo_settings* settings, float dt, uint32_t begin, uint32_t end);
+void xo_phase_elems(xo_scene* s, const xo_settings* settings, float dt, int kind, const uint32_t* elems, uint32_t count);
 void xo_phase_post(xo_scene* s, const xo_settings* settings, const xo_manipulator* manip, float dt);
 void xo_set_flags(xo_scene* s, const uint8_t* flags);
 void xo_set_ground(xo_scene* s, int enabled, float y0, float friction);

@@ -89,7 +89,6 @@ def reference_state(order, n):
 
 
 if a.mode == "emulate":
-    assert not GENERAL, "the emulation covers the main sweep; damping / volume passes are checked on the GPUs"
     from oracle import bindings as ob
     dist.init_process_group("gloo")
     part = xf.GeoPartitionCuda(nodes, idx, world, rank, device=-1, color_hint=hint, partition=PARTITION, density=DENSITY, auto_resize=AUTO_RESIZE)
@@ -111,30 +110,72 @@ if a.mode == "emulate":
     sub.copy_elements_from(full, elems, rest=X0full[l2g])
     sub.set_state(w=w)
     sub.set_flags(flags)
-    st = ob.make_settings(**kw)
-    for s in range(a.substeps):
-        sub.phase_predict(st, DT)
-        for c in range(part.nColors):
-            sub.phase_sweep(st, DT, int(cs[c]), int(cs[c + 1]))
-            X, V, ww = sub.get_state()
-            reqs, bufs = [], []
-            for slot, q in enumerate(peers):
-                snd = part.halo(c, slot, True)
-                rcv = part.halo(c, slot, False)
-                out = torch.from_numpy(np.ascontiguousarray(X[snd]))
-                inn = torch.empty((len(rcv), 3), dtype=torch.float64)
-                if len(snd):
-                    reqs.append(dist.isend(out, int(q), tag=c))
-                if len(rcv):
-                    reqs.append(dist.irecv(inn, int(q), tag=c))
-                bufs.append((rcv, inn, out))
-            for r in reqs:
-                r.wait()
-            for rcv, inn, _ in bufs:
-                if len(rcv):
-                    X[rcv] = inn.numpy()
-            sub.set_state(X=X)
-        sub.phase_post(st, DT)
+    # global serial position of every local element (the amortised damping slices are ranges of the FULL mesh's serial order)
+    full_order = part.get_order()
+    serial_pos = np.empty(part.nTGlobal, dtype=np.int64)
+    serial_pos[full_order] = np.arange(part.nTGlobal)
+    local_pos = serial_pos[elems]
+    gcs = part.global_color_start()
+    tag = [0]
+
+    def exchange(c, which):
+        """after a phase of colour c: push the values of the vertices this rank's elements of that colour touch to the other copies"""
+        X, V, ww = sub.get_state()
+        arr = X if which == "X" else V
+        reqs, bufs = [], []
+        tag[0] += 1
+        for slot, q in enumerate(peers):
+            snd = part.halo(c, slot, True)
+            rcv = part.halo(c, slot, False)
+            out = torch.from_numpy(np.ascontiguousarray(arr[snd]))
+            inn = torch.empty((len(rcv), 3), dtype=torch.float64)
+            if len(snd):
+                reqs.append(dist.isend(out, int(q), tag=tag[0]))
+            if len(rcv):
+                reqs.append(dist.irecv(inn, int(q), tag=tag[0]))
+            bufs.append((rcv, inn, out))
+        for r in reqs:
+            r.wait()
+        for rcv, inn, _ in bufs:
+            if len(rcv):
+                arr[rcv] = inn.numpy()
+        if which == "X":
+            sub.set_state(X=arr)
+        else:
+            sub.set_state(V=arr)
+
+    def emulate(st, n):
+        rayleigh = (st.flags >> ob.Settings_RayleighTypeBit) & 3
+        do_damp = rayleigh >= 2 and st.damping > 0.0
+        do_pbd = st.pbdDamping > 0.0
+        for s_ in range(n):
+            sub.phase_predict(st, DT)
+            for c in range(part.nColors):
+                sub.phase_elems(st, DT, 0, np.arange(cs[c], cs[c + 1]))
+                exchange(c, "X")
+            for _ in range(st.volumePasses):
+                for c in range(part.nColors):
+                    sub.phase_elems(st, DT, 1, np.arange(cs[c], cs[c + 1]))
+                    exchange(c, "X")
+            sub.phase_post(st, DT)
+            if do_damp or do_pbd:
+                lo, hi = 0, part.nTGlobal
+                if rayleigh == 3:
+                    k = st.tickId % 8
+                    lo, hi = part.nTGlobal * k // 8, part.nTGlobal * (k + 1) // 8
+                for kind, on in ((2, do_damp), (3, do_pbd)):
+                    if not on:
+                        continue
+                    for c in range(part.nColors):
+                        if not (gcs[c] < hi and gcs[c + 1] > lo):
+                            continue  # the same verdict on every rank
+                        mine = np.arange(cs[c], cs[c + 1])
+                        mine = mine[(local_pos[mine] >= lo) & (local_pos[mine] < hi)]
+                        sub.phase_elems(st, DT, kind, mine)
+                        exchange(c, "V")
+            st.tickId += 1
+
+    run_calls(sub, ob.make_settings, lambda sc, st, k: emulate(st, k))
     X, V, ww = sub.get_state()
     order = part.get_order()
 else:

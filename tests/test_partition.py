@@ -146,6 +146,17 @@ def test_graph_partition_plan_is_balanced_and_connected():
         assert not p.dataflow_codes()[2] or world <= 2  # more than two copies of some vertex: the flag protocol applies
 
 
+@pytest.mark.parametrize("world,extra", [(2, ["--damping", "0.005", "--rayleigh", "3"]), (3, ["--damping", "0.005", "--rayleigh", "2", "--energy", "4"]),
+                                         (2, ["--volume-passes", "2", "--energy", "4", "--poisson", "0.495"]),
+                                         (3, ["--damping", "0.005", "--rayleigh", "3", "--volume-passes", "1", "--mix", "--partition", "graph",
+                                              "--dims", "9", "4"])])
+def test_partitioned_damping_emulation_matches_single_scene_oracle(world, extra):
+    """Damping sweeps over amortised slices of the GLOBAL serial order, PBD damping and volume passes on a partitioned mesh, emulated on
+    CPU (velocities of shared vertices exchanged after every damping phase, as the GPUs mirror them): bit-exact against the oracle."""
+    out = run_ranks(world, ["--mode", "emulate", "--dims", "8", "3", "--substeps", "19"] + extra, 29661 + world)
+    assert out["ok"], out["msg"]
+
+
 def gpu_count():
     try:
         return xf.device_count()
