@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=55, help="block is cells^3 hexes -> 6*cells^3 tets")
     ap.add_argument("--substeps-per-step", type=int, default=50)
     ap.add_argument("--precision", choices=["exact", "fast"], default="exact")
-    ap.add_argument("--schedule", choices=["dataflow", "bricks", "persistent", "per_color"], default="dataflow")
+    ap.add_argument("--schedule", choices=["dataflow", "persistent", "per_color"], default="dataflow")
     ap.add_argument("--grouping", choices=["auto", "elements", "chains", "clusters"], default="auto",
                     help="xf_grouping: chains = vertex records shared with the thread's next element stay in private shared memory")
     ap.add_argument("--energy", choices=["yeohskinfast", "mixedsel", "mixed", "yeohskin"], default="yeohskinfast")
@@ -147,7 +147,7 @@ def make_scene(xf, args, device, stream):
         hint = (4 * (hint % 6) + hint // 6).astype(hint.dtype)
     geo = xf.GeoLinear3dCuda(nodes, idx, device=device, stream=stream,
                              precision=xf.PRECISION_EXACT if args.precision == "exact" else xf.PRECISION_FAST,
-                             schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "bricks": xf.SCHEDULE_BRICKS, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
+                             schedule={"dataflow": xf.SCHEDULE_DATAFLOW, "persistent": xf.SCHEDULE_PERSISTENT, "per_color": xf.SCHEDULE_LAUNCH_PER_COLOR}[args.schedule],
                              color_hint=None if args.no_hint else hint,
                              grouping={"auto": xf.GROUPING_AUTO, "elements": xf.GROUPING_ELEMENTS, "chains": xf.GROUPING_CHAINS,
                                        "clusters": xf.GROUPING_CLUSTERS}[args.grouping])
@@ -607,7 +607,7 @@ def main():
         ach_hbm = (nT * sub * b_hbm) / (kernel_ms * 1e-3) / 1e9
         ach_l2 = (nT * sub * b_l2) / (kernel_ms * 1e-3) / 1e9
         ws = 56 * nT + 48 * nV
-        kernel = info.get("lastKernel") or {"dataflow": "k_substeps_dataflow", "bricks": "k_substeps_bricks", "persistent": "k_substeps_persistent",
+        kernel = info.get("lastKernel") or {"dataflow": "k_substeps_dataflow", "persistent": "k_substeps_persistent",
                                             "per_color": "k_sweep_color (x colours)"}[args.schedule]
         traffic, traffic_src = load_traffic(kernel, args)
         roofline = {

@@ -127,7 +127,7 @@ typedef enum xf_schedule {
 	XF_SCHEDULE_AUTO = 0,
 	XF_SCHEDULE_LAUNCH_PER_COLOR = 1, /* one kernel launch per colour phase */
 	XF_SCHEDULE_PERSISTENT = 2,       /* one cooperative launch per xf_substep call, grid barriers between colours */
-	XF_SCHEDULE_BRICKS = 3,           /* PERSISTENT + vertices private to a CTA's brick of elements kept in shared memory */
+	XF_SCHEDULE_BRICKS = 3,           /* retired in round 2 (measured slower than PERSISTENT): accepted, runs as XF_SCHEDULE_PERSISTENT */
 	XF_SCHEDULE_DATAFLOW = 4          /* one co-resident launch, NO barriers: vertex records carry the stage that wrote them and
 	                                     every element re-gathers until its four records carry the expected stage.  Same serial
 	                                     order and bits as the others, also with volume passes and post-solve damping sweeps
@@ -250,7 +250,7 @@ typedef enum xf_kernel_id {
 	XF_KERNEL_CHAIN = 2,         /* k_substeps_chain */
 	XF_KERNEL_CLUSTER = 3,       /* k_substeps_cluster */
 	XF_KERNEL_PERSISTENT = 4,    /* k_substeps_persistent: grid barrier per colour */
-	XF_KERNEL_BRICKS = 5,        /* k_substeps_bricks */
+	XF_KERNEL_BRICKS = 5,        /* retired (never reported) */
 	XF_KERNEL_PER_COLOR = 6,     /* k_sweep_color / k_vertex_phase, one launch per colour */
 	XF_KERNEL_DATAFLOW_GENERAL = 7 /* k_substeps_dataflow_general: barrier-free with volume passes / post-solve damping sweeps */
 } xf_kernel_id;

@@ -111,7 +111,7 @@ def test_frames_stepped_on_device_match_reference_sim(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR, xf.SCHEDULE_BRICKS])
+@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR])
 def test_substep_varying_equals_single_substeps(schedule):
     """xf_substep_varying (one launch, per-substep lock transform + manipulator ray) against the same substeps issued one by one
     on the oracle, with damping sweeps (k_substeps_dataflow_general) and without."""

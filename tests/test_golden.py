@@ -66,7 +66,7 @@ def make_geo(d, precision, schedule):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_BRICKS, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR])
+@pytest.mark.parametrize("schedule", [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR])
 @pytest.mark.parametrize("path", COLOUR_FIXTURES, ids=[os.path.basename(p)[:-4] for p in COLOUR_FIXTURES])
 def test_cuda_exact_replays_reference_goldens(path, schedule):
     d, _, st = load(path)

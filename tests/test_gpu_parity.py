@@ -17,7 +17,7 @@ build()
 xf = load_package()
 pytestmark = pytest.mark.gpu
 DT = np.float32(1.0 / 3000.0)
-SCHEDULES = [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_BRICKS, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
+SCHEDULES = [xf.SCHEDULE_DATAFLOW, xf.SCHEDULE_PERSISTENT, xf.SCHEDULE_LAUNCH_PER_COLOR]
 if os.environ.get("XF_TEST_SCHEDULES"):  # development aid: restrict the schedule axis, e.g. XF_TEST_SCHEDULES=4
     SCHEDULES = [int(x) for x in os.environ["XF_TEST_SCHEDULES"].split(",")]
 

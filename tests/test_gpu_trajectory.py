@@ -198,7 +198,7 @@ def big():
 def test_full_size_properties(big):
     nodes, idx, hint = big
     st = xf.make_settings(energy=xf.Energy_YeohSkinFast, poisson=0.5)
-    a = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_BRICKS, color_hint=hint)
+    a = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_BRICKS, color_hint=hint)  # retired: runs as PERSISTENT
     b = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_LAUNCH_PER_COLOR, color_hint=hint)
     p = xf.GeoLinear3dCuda(nodes, idx, schedule=xf.SCHEDULE_PERSISTENT, color_hint=hint)
     p.Substep(st, DT, 60)

@@ -35,7 +35,6 @@ namespace {
 // XF_GROUPING_AUTO on the barrier-free schedule: chained sweep or plain one element per thread
 constexpr bool kChainByDefault = false;
 constexpr uint32_t kChainMinPermille = 100;
-constexpr uint32_t kBrickSlotCap = 3000; // private vertices per CTA kept in shared memory (96 KB; 2 CTAs per SM)
 
 template <typename T>
 cudaError_t Upload(T** dst, const std::vector<T>& src) {
@@ -90,7 +89,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAb, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eK, d.extOfInt, d.canonPos, d.brickStart, d.privStart, d.privVerts, d.sharedVerts, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eK, d.extOfInt, d.canonPos, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW, s->dVary };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->stallWord) { cudaFreeHost((void*)s->stallWord); }
@@ -103,11 +102,8 @@ int UploadScene(xf_scene* s) {
 	d.nV = m.nV;
 	d.nT = m.nT;
 	d.nColors = (uint32_t)m.colorStart.size() - 1;
-	// element planes: colour-major; inside a colour in stream order, or (XF_SCHEDULE_BRICKS) grouped by brick, one brick
-	// per CTA of the persistent grid (2 CTAs x 256 threads per SM)
-	const bool bricks = s->schedule == XF_SCHEDULE_BRICKS;
-	BrickPlan bp;
-	BuildBricks(m, bricks ? (uint32_t)(2 * s->smCount) : 1u, kBrickSlotCap, &bp);
+	// element planes: colour-major, inside a colour in stream order = the serial order of xf_get_order
+	const std::vector<uint32_t>& deviceOrder = m.order;
 	// Device vertex numbering.  A warp handles 32 consecutive elements of one colour and its lanes gather/scatter corner n
 	// of their element with one 256-bit access each; every distinct 128-byte line costs one L1TEX wavefront, and the sweep's
 	// per-element cost IS those wavefronts (~276 per warp-element when every lane hits its own line).  Numbering the vertices
@@ -117,11 +113,11 @@ int UploadScene(xf_scene* s) {
 	s->intOfExt.assign(m.nV, 0xffffffffu);
 	s->extOfInt.clear();
 	s->extOfInt.reserve(m.nV);
-	if (!bricks && !getenv("XF_NO_RENUMBER")) {
+	if (!getenv("XF_NO_RENUMBER")) {
 		for (uint32_t c = 0; c < d.nColors; c++) {
 			for (int j = 0; j < 4; j++) {
 				for (uint32_t k = m.colorStart[c]; k < m.colorStart[c + 1]; k++) {
-					const uint32_t v = m.idx[4 * (size_t)bp.deviceOrder[k] + j];
+					const uint32_t v = m.idx[4 * (size_t)deviceOrder[k] + j];
 					if (s->intOfExt[v] == 0xffffffffu) { s->intOfExt[v] = (uint32_t)s->extOfInt.size(); s->extOfInt.push_back(v); }
 				}
 			}
@@ -144,27 +140,22 @@ int UploadScene(xf_scene* s) {
 	XF_CUDA(Upload(&d.extOfInt, s->extOfInt));
 	std::vector<uint32_t> streamToSorted(m.nT), canonPos(m.nT), serialPos(m.nT);
 	for (uint32_t pos = 0; pos < m.nT; pos++) { serialPos[m.order[pos]] = pos; }
-	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[bp.deviceOrder[pos]] = pos; canonPos[pos] = serialPos[bp.deviceOrder[pos]]; }
+	for (uint32_t pos = 0; pos < m.nT; pos++) { streamToSorted[deviceOrder[pos]] = pos; canonPos[pos] = serialPos[deviceOrder[pos]]; }
 	std::vector<uint32_t> devIdx(4 * (size_t)m.nT);
 	for (uint32_t k = 0; k < m.nT; k++) {
-		for (int j = 0; j < 4; j++) { devIdx[4 * (size_t)k + j] = s->intOfExt[m.idx[4 * (size_t)bp.deviceOrder[k] + j]]; }
+		for (int j = 0; j < 4; j++) { devIdx[4 * (size_t)k + j] = s->intOfExt[m.idx[4 * (size_t)deviceOrder[k] + j]]; }
 	}
 	PackedElements pk;
-	PackElements(m, bp.deviceOrder, devIdx.data(), &pk);
+	PackElements(m, deviceOrder, devIdx.data(), &pk);
 	XF_CUDA(Upload(&d.eA, pk.a));
 	XF_CUDA(Upload(&d.eB, pk.b));
 	XF_CUDA(Upload(&d.eC, pk.c));
 	XF_CUDA(Upload(&d.eArea, pk.area));
-	if (bricks) { // identity vertex numbering here: the brick plan speaks the caller's ids
-		PackedElements pkb;
-		PackElements(m, bp.deviceOrder, bp.encodedIdx.data(), &pkb);
-		XF_CUDA(Upload(&d.eAb, pkb.a));
-	}
 	// dataflow schedule: previous-writer stage code per (element, vertex) in the top byte of the index, last-writer code per vertex
 	s->dataflowOk = m.nV <= 0x01000000u && d.nColors <= 254u;
 	if (s->dataflowOk) {
 		std::vector<uint8_t> pred, lastExt, lastCode(m.nV, 0);
-		StageCodes(m, bp.deviceOrder, &pred, &lastExt);
+		StageCodes(m, deviceOrder, &pred, &lastExt);
 		std::vector<ElemRecA> ad = pk.a;
 		for (uint32_t k = 0; k < m.nT; k++) {
 			for (int j = 0; j < 4; j++) { ad[k].idx[j] = pk.a[k].idx[j] | ((uint32_t)pred[4 * (size_t)k + j] << 24); }
@@ -174,14 +165,14 @@ int UploadScene(xf_scene* s) {
 		XF_CUDA(Upload(&d.lastCode, lastCode));
 		if (m.groupSize > 1) { // clustered colouring: slot / first / last bits of every corner, device order
 			std::vector<uint32_t> ek(m.nT);
-			for (uint32_t k = 0; k < m.nT; k++) { ek[k] = m.clusterInfo[bp.deviceOrder[k]]; }
+			for (uint32_t k = 0; k < m.nT; k++) { ek[k] = m.clusterInfo[deviceOrder[k]]; }
 			XF_CUDA(Upload(&d.eK, ek));
 			d.groupSize = m.groupSize;
-		} else if (!s->chainInfo.empty() && !bricks && bp.deviceOrder == m.order) { // chained sweep: device order == serial order
+		} else if (!s->chainInfo.empty()) { // chained sweep: device order == serial order
 			XF_CUDA(Upload(&d.eK, s->chainInfo));
 			d.chained = 1;
 		}
-		if (!bricks && m.groupSize <= 1 && bp.deviceOrder == m.order) {
+		if (m.groupSize <= 1) {
 			// damping sweeps on the barrier-free schedule (xf_dataflow_general.cu): V records are versioned by a write count.
 			// Rank of every element among the elements around each of its corners' vertices (serial order), and per vertex how
 			// many of those elements lie below each boundary nT*q/8 of the amortised damping slices (Geo.cpp:794-797).
@@ -207,15 +198,6 @@ int UploadScene(xf_scene* s) {
 		if (const char* env = getenv("XF_DATAFLOW_BLOCK")) { d.dataflowBlock = (uint32_t)atoi(env); }
 	}
 	XF_CUDA(Upload(&d.canonPos, canonPos));
-	if (bricks) {
-		XF_CUDA(Upload(&d.brickStart, bp.brickStart));
-		XF_CUDA(Upload(&d.privStart, bp.privStart));
-		XF_CUDA(Upload(&d.privVerts, bp.privVerts));
-		XF_CUDA(Upload(&d.sharedVerts, bp.sharedVerts));
-		d.nBricks = bp.nBricks;
-		d.nSharedVerts = (uint32_t)bp.sharedVerts.size();
-		d.maxPrivPerBrick = bp.maxPrivPerBrick;
-	}
 	XF_CUDA(Upload(&d.streamToSorted, streamToSorted));
 	XF_CUDA(cudaMalloc((void**)&d.eScratch, sizeof(float) * m.nT));
 	XF_CUDA(cudaMalloc((void**)&d.statScratch, sizeof(double) * 8));
@@ -352,7 +334,11 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		if (const char* env = getenv("XF_DATAFLOW_SLEEP_NS")) { s->spinSleepNs = (uint32_t)atoi(env) & 0x7fffu; }
 		if (getenv("XF_DATAFLOW_NO_PREFETCH")) { s->spinSleepNs |= 0x8000u; }
 		if (const char* env = getenv("XF_DATAFLOW_ESLEEP_NS")) { s->spinSleepNs |= ((uint32_t)atoi(env) & 0xffffu) << 16; }
-		if (s->schedule == XF_SCHEDULE_AUTO) { // BRICKS measured slower, see xf_bricks.cu
+		// XF_SCHEDULE_BRICKS (vertices private to a CTA's Morton brick kept in shared memory, round 1) measured slower than the
+		// plain grid-barrier kernel (99.6 vs 92.4 us per substep at 1M tets, profiles/r1_results.md) and was retired in round 2:
+		// the value is still accepted and runs as XF_SCHEDULE_PERSISTENT (same serial order, same bits).
+		if (s->schedule == XF_SCHEDULE_BRICKS) { s->schedule = XF_SCHEDULE_PERSISTENT; }
+		if (s->schedule == XF_SCHEDULE_AUTO) {
 			s->schedule = !s->cooperative ? XF_SCHEDULE_LAUNCH_PER_COLOR : (s->dataflowOk ? XF_SCHEDULE_DATAFLOW : XF_SCHEDULE_PERSISTENT);
 		}
 		if (s->schedule == XF_SCHEDULE_DATAFLOW && !s->dataflowOk) {
@@ -361,7 +347,7 @@ int xf_create(const xf_create_params* params, const float* nodeXYZ, uint32_t nod
 		}
 		if (s->schedule >= XF_SCHEDULE_PERSISTENT && !s->cooperative) {
 			FreeDevice(s); delete s;
-			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT / BRICKS / DATAFLOW)");
+			return Fail(XF_ERR_UNSUPPORTED, "device does not support cooperative launches (needed by XF_SCHEDULE_PERSISTENT / DATAFLOW)");
 		}
 	}
 	*outScene = s;
@@ -453,9 +439,6 @@ static int LaunchSubsteps(xf_scene* s, SubstepParams& p, uint32_t firstTick, uin
 			s->verBase = (s->verBase + m * stride + 1u) & 0x00ffffffu;
 			done += m;
 		}
-	} else if (s->schedule == XF_SCHEDULE_BRICKS) {
-		s->lastKernel = XF_KERNEL_BRICKS;
-		XF_CUDA(LaunchSubstepsBricks(s->dev, p, exact, n, s->smCount, s->stream, &s->launches));
 	} else if (s->schedule == XF_SCHEDULE_PERSISTENT || s->schedule == XF_SCHEDULE_DATAFLOW) {
 		auto it = s->shapes.find(p.energy);
 		if (it == s->shapes.end()) {
@@ -733,10 +716,7 @@ int xf_get_info(const xf_scene* s, xf_info* out) {
 	out->maxColorSize = mx;
 	out->smCount = (uint32_t)s->smCount;
 	out->chainedPermille = s->device < 0 || (s->dev.chained && s->schedule == XF_SCHEDULE_DATAFLOW) ? s->chainedPermille : 0;
-	if (s->schedule == XF_SCHEDULE_BRICKS) {
-		out->gridBlocks = s->dev.nBricks;
-		out->blockThreads = 256;
-	} else if (s->schedule == XF_SCHEDULE_DATAFLOW) {
+	if (s->schedule == XF_SCHEDULE_DATAFLOW) {
 		out->gridBlocks = (uint32_t)(2 * s->smCount);
 		out->blockThreads = s->dev.groupSize > 1 ? 256u : (uint32_t)DataflowBlockThreads(s->dev, 2 * s->smCount);
 	} else if (!s->shapes.empty()) {

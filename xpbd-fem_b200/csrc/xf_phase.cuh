@@ -1,4 +1,4 @@
-// Device functions shared by the sweep kernels (xf_kernels.cu) and the brick kernel (xf_bricks.cu): the vertex
+// Device functions shared by the sweep kernels (xf_kernels.cu, xf_dataflow*.cu): the vertex
 // phase and the damping-slice helpers.
 #pragma once
 
@@ -103,8 +103,8 @@ __device__ __forceinline__ void VertexPhase(const DeviceScene& sc, const Substep
 	StoreVertex(sc.Xw, i, v);
 }
 
-// Damping sweeps act on the slice [lo, hi) of the SERIAL order (Geo.cpp:794-797); inside a colour the device planes
-// are grouped by brick, so membership is decided per element from its serial position.
+// Damping sweeps act on the slice [lo, hi) of the SERIAL order (Geo.cpp:794-797); on a partitioned mesh the local planes hold a
+// subset of it, so membership is decided per element from its (global) serial position.
 __device__ __forceinline__ bool InSlice(const DeviceScene& sc, uint32_t e, uint32_t lo, uint32_t hi) {
 	const uint32_t pos = __ldg(sc.canonPos + e);
 	return pos >= lo && pos < hi;

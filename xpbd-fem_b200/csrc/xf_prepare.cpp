@@ -417,88 +417,6 @@ int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* i
 	return XF_OK;
 }
 
-namespace {
-inline uint32_t Spread10(uint32_t v) { // 10 bits -> every third bit
-	v &= 0x3ffu;
-	v = (v | (v << 16)) & 0x030000ffu;
-	v = (v | (v << 8)) & 0x0300f00fu;
-	v = (v | (v << 4)) & 0x030c30c3u;
-	v = (v | (v << 2)) & 0x09249249u;
-	return v;
-}
-}  // namespace
-
-void BuildBricks(const HostMesh& m, uint32_t nBricks, uint32_t slotCap, BrickPlan* out) {
-	BrickPlan& bp = *out;
-	bp.nBricks = nBricks;
-	const uint32_t nColors = (uint32_t)m.colorStart.size() - 1;
-	// 1. Morton order of the element centroids in the rest pose -> nBricks equal chunks
-	double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-	for (uint32_t i = 0; i < m.nV; i++) {
-		for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], m.X0[3 * (size_t)i + k]); hi[k] = std::max(hi[k], m.X0[3 * (size_t)i + k]); }
-	}
-	std::vector<uint32_t> code(m.nT);
-	for (uint32_t e = 0; e < m.nT; e++) {
-		uint32_t q[3];
-		for (int k = 0; k < 3; k++) {
-			double c = 0.0;
-			for (int j = 0; j < 4; j++) { c += m.X0[3 * (size_t)m.idx[4 * (size_t)e + j] + k]; }
-			const double rel = hi[k] > lo[k] ? (0.25 * c - lo[k]) / (hi[k] - lo[k]) : 0.0;
-			q[k] = (uint32_t)std::min(1023.0, std::max(0.0, rel * 1024.0));
-		}
-		code[e] = Spread10(q[0]) | (Spread10(q[1]) << 1) | (Spread10(q[2]) << 2);
-	}
-	std::vector<uint32_t> byCode(m.nT);
-	std::iota(byCode.begin(), byCode.end(), 0u);
-	std::stable_sort(byCode.begin(), byCode.end(), [&](uint32_t a, uint32_t b) { return code[a] < code[b]; });
-	std::vector<uint32_t> brickOf(m.nT);
-	for (uint32_t k = 0; k < m.nT; k++) { brickOf[byCode[k]] = (uint32_t)(((uint64_t)k * nBricks) / m.nT); }
-	// 2. private vertices: touched by exactly one brick (0xfffffffe = several)
-	std::vector<uint32_t> owner(m.nV, 0xffffffffu);
-	for (uint32_t e = 0; e < m.nT; e++) {
-		for (int j = 0; j < 4; j++) {
-			uint32_t& o = owner[m.idx[4 * (size_t)e + j]];
-			if (o == 0xffffffffu) { o = brickOf[e]; } else if (o != brickOf[e]) { o = 0xfffffffeu; }
-		}
-	}
-	std::vector<uint32_t> slot(m.nV, 0xffffffffu), count(nBricks, 0);
-	for (uint32_t v = 0; v < m.nV; v++) {
-		const uint32_t o = owner[v];
-		if (o < nBricks && count[o] < slotCap) { slot[v] = count[o]++; }
-	}
-	bp.privStart.assign(nBricks + 1, 0);
-	for (uint32_t b = 0; b < nBricks; b++) { bp.privStart[b + 1] = bp.privStart[b] + count[b]; bp.maxPrivPerBrick = std::max(bp.maxPrivPerBrick, count[b]); }
-	bp.privVerts.assign(bp.privStart[nBricks], 0);
-	bp.sharedVerts.clear();
-	for (uint32_t v = 0; v < m.nV; v++) {
-		if (slot[v] != 0xffffffffu) { bp.privVerts[bp.privStart[owner[v]] + slot[v]] = v; } else { bp.sharedVerts.push_back(v); }
-	}
-	// 3. device arrangement: colour-major, brick-minor, stream index inside
-	bp.deviceOrder.resize(m.nT);
-	bp.brickStart.assign((size_t)nColors * nBricks + 1, 0);
-	for (uint32_t c = 0; c < nColors; c++) {
-		for (uint32_t k = m.colorStart[c]; k < m.colorStart[c + 1]; k++) { bp.brickStart[(size_t)c * nBricks + brickOf[m.order[k]] + 1]++; }
-	}
-	for (size_t k = 0; k + 1 < bp.brickStart.size(); k++) { bp.brickStart[k + 1] += bp.brickStart[k]; }
-	{
-		std::vector<uint32_t> cursor(bp.brickStart.begin(), bp.brickStart.end() - 1);
-		for (uint32_t c = 0; c < nColors; c++) {
-			for (uint32_t k = m.colorStart[c]; k < m.colorStart[c + 1]; k++) {
-				const uint32_t e = m.order[k];
-				bp.deviceOrder[cursor[(size_t)c * nBricks + brickOf[e]]++] = e;
-			}
-		}
-	}
-	bp.encodedIdx.resize(4 * (size_t)m.nT);
-	for (uint32_t k = 0; k < m.nT; k++) {
-		const uint32_t e = bp.deviceOrder[k];
-		for (int j = 0; j < 4; j++) {
-			const uint32_t v = m.idx[4 * (size_t)e + j];
-			bp.encodedIdx[4 * (size_t)k + j] = slot[v] != 0xffffffffu ? (0x80000000u | slot[v]) : v;
-		}
-	}
-}
-
 void StageCodes(const HostMesh& m, const std::vector<uint32_t>& order, std::vector<uint8_t>* pred, std::vector<uint8_t>* last) {
 	pred->assign(4 * (size_t)m.nT, 0);
 	last->assign(m.nV, 0);

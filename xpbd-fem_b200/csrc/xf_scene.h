@@ -56,16 +56,7 @@ struct DeviceScene {
 	float* eScratch = nullptr;      // nT floats (per-element volume terms)
 	double* statScratch = nullptr;  // reduction outputs
 	uint32_t* streamToSorted = nullptr; // nT: position of stream element s in the colour-sorted planes
-	uint32_t* canonPos = nullptr;       // nT: position in the serial order (xf_get_order) of the element at device position k
-	// brick schedule (XF_SCHEDULE_BRICKS): inside a colour the planes are grouped by brick (= CTA of the persistent grid)
-	uint32_t nBricks = 0;
-	ElemRecA* eAb = nullptr;            // eA with private vertices encoded as 0x80000000 | shared-memory slot
-	uint32_t* brickStart = nullptr;     // nColors * nBricks + 1 offsets into the planes
-	uint32_t* privStart = nullptr;      // nBricks + 1 offsets into privVerts
-	uint32_t* privVerts = nullptr;      // global vertex id of every shared-memory slot
-	uint32_t* sharedVerts = nullptr;    // vertices touched by more than one brick (stay in L2)
-	uint32_t nSharedVerts = 0;
-	uint32_t maxPrivPerBrick = 0;
+	uint32_t* canonPos = nullptr;       // nT: position in the serial order (xf_get_order) of the element at device position k (identity on one GPU; global position on a partition)
 	unsigned int* barrier = nullptr; // grid-barrier counter
 	// Stall report of the barrier-free schedules.  A record that never reaches the expected stage (a broken schedule, or a caller
 	// that rewrote the state under a running launch) must not hang the device and must not kill the CUDA context either: the warp
@@ -199,21 +190,6 @@ struct HostMesh {
 	std::vector<uint32_t> clusterInfo;
 };
 
-// Brick plan (xf_prepare.cpp): elements are grouped into `nBricks` spatially compact chunks (Morton order of the
-// rest-pose centroids), one per CTA of the persistent grid.  A vertex touched by a single brick is *private*: it
-// lives in that CTA's shared memory for the whole launch, so most gathers/scatters never reach L2.
-struct BrickPlan {
-	uint32_t nBricks = 0;
-	std::vector<uint32_t> deviceOrder;  // global element ids: colour-major, brick-minor
-	std::vector<uint32_t> brickStart;   // nColors * nBricks + 1
-	std::vector<uint32_t> encodedIdx;   // 4 per element (device order): global id, or 0x80000000 | slot
-	std::vector<uint32_t> privStart;    // nBricks + 1
-	std::vector<uint32_t> privVerts;
-	std::vector<uint32_t> sharedVerts;
-	uint32_t maxPrivPerBrick = 0;
-};
-void BuildBricks(const HostMesh& mesh, uint32_t nBricks, uint32_t slotCap, BrickPlan* out);
-
 // Returns 0 or an xf_status; on failure `err` holds the message.
 int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* idxStream, uint32_t idxCount, float density,
                 bool autoResize, const uint32_t* colorHint, uint32_t colorHintCount, HostMesh* out, std::string* err, bool clustered = false);
@@ -247,8 +223,6 @@ int FailCuda(cudaError_t e, const char* what);
 cudaError_t QueryLaunchShape(int device, uint32_t energy, bool exact, LaunchShape* shape);
 cudaError_t LaunchSubstepsPerColor(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, cudaStream_t stream,
                                    uint64_t* launchCount);
-cudaError_t LaunchSubstepsBricks(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, cudaStream_t stream,
-                                 uint64_t* launchCount);
 cudaError_t LaunchSubstepsDataflow(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, int smCount, uint32_t verBase,
                                    uint32_t sleepNs, cudaStream_t stream, uint64_t* launchCount);
 // Falls back to LaunchSubstepsDataflow when a colour does not fit one wave of the grid.
