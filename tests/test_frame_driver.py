@@ -94,6 +94,7 @@ def test_frames_stepped_on_device_match_reference_sim(case):
     state = xf.new_frame_state()
     mx = picked_manip(xf.Manipulator, 40) if case == "picked" else None
     mo = picked_manip(ob.Manipulator, 40) if case == "picked" else None
+    stepped = False
     for k, (dt, med) in enumerate(FRAMES):
         if case == "lock_right_rotating":
             sx.leftRightSeparation = so.leftRightSeparation = 1.0 - 0.03 * k
@@ -101,8 +102,11 @@ def test_frames_stepped_on_device_match_reference_sim(case):
         before = geo.info()["kernelLaunches"]
         n = geo.FrameUpdate(sx, np.float32(dt), np.float32(med), state, manip=mx)
         assert n == n_ref
-        # one launch per frame, also while dragging or animating the lock (per-substep rows on the device, xf_substep_varying)
-        assert geo.info()["kernelLaunches"] - before == (1 if n else 0), "frame %d took %d launches for %d substeps" % (
+        # one launch per frame, also while dragging or animating the lock (per-substep rows on the device, xf_substep_varying);
+        # the first stepped frame also evaluates the per-element alpha plane for its (compliance, nu, dt) once
+        extra = 1 if (n and not stepped) else 0
+        stepped = stepped or n > 0
+        assert geo.info()["kernelLaunches"] - before == (1 if n else 0) + extra, "frame %d took %d launches for %d substeps" % (
             k, geo.info()["kernelLaunches"] - before, n)
         Xg, Vg, wg = geo.get_state()
         Xr, Vr, wr = sim.get_state()

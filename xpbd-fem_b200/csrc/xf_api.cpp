@@ -67,6 +67,8 @@ struct xf_scene {
 	uint64_t launches = 0;
 	uint32_t lastKernel = 0;  // xf_kernel_id of the last stepping launch
 	uint64_t vEpoch = 1;      // substeps stepped by k_substeps_dataflow_general so far (V-record tags)
+	float alphaKey[3] = { 0.0f, 0.0f, 0.0f }; // (invMu, invLambda, dt2) the alpha plane (DeviceScene::eAlpha) was computed for
+	bool alphaValid = false;
 	float* dVary = nullptr;   // per-substep parameter rows of xf_substep_varying (kVaryFloats floats each)
 	size_t dVaryRows = 0;
 	// extensions
@@ -89,7 +91,7 @@ void FreeDevice(xf_scene* s) {
 	if (s->device < 0) { return; }
 	cudaSetDevice(s->device);
 	DeviceScene& d = s->dev;
-	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eK, d.extOfInt, d.canonPos, d.eScratch, d.statScratch, d.streamToSorted,
+	void* ptrs[] = { d.Xw, d.O, d.V, d.X0, d.eA, d.eB, d.eC, d.eArea, d.eAd, d.lastCode, d.eRank, d.vSlice, d.eAlpha, d.eK, d.extOfInt, d.canonPos, d.eScratch, d.statScratch, d.streamToSorted,
 		             d.barrier, s->dPackX, s->dPackV, s->dPackW, s->dVary };
 	for (void* p : ptrs) { if (p) { cudaFree(p); } }
 	if (s->stallWord) { cudaFreeHost((void*)s->stallWord); }
@@ -163,6 +165,7 @@ int UploadScene(xf_scene* s) {
 		for (uint32_t v = 0; v < m.nV; v++) { lastCode[s->intOfExt[v]] = lastExt[v]; }
 		XF_CUDA(Upload(&d.eAd, ad));
 		XF_CUDA(Upload(&d.lastCode, lastCode));
+		XF_CUDA(cudaMalloc((void**)&d.eAlpha, sizeof(float2) * std::max<size_t>(m.nT, 1)));
 		if (m.groupSize > 1) { // clustered colouring: slot / first / last bits of every corner, device order
 			std::vector<uint32_t> ek(m.nT);
 			for (uint32_t k = 0; k < m.nT; k++) { ek[k] = m.clusterInfo[deviceOrder[k]]; }
@@ -418,6 +421,11 @@ static int LaunchSubsteps(xf_scene* s, SubstepParams& p, uint32_t firstTick, uin
 	const bool generalOk = !inConstraintDamping && s->dev.eRank && !s->dev.chained && s->dev.groupSize <= 1 && !getenv("XF_NO_DATAFLOW_GENERAL");
 	const float* vary0 = p.vary;
 	if (s->schedule == XF_SCHEDULE_DATAFLOW && (plainSweep || generalOk)) {
+		if (!(s->alphaValid && s->alphaKey[0] == p.invMu && s->alphaKey[1] == p.invLambda && s->alphaKey[2] == p.dt2)) {
+			XF_CUDA(LaunchElementAlpha(s->dev, p, exact, s->stream, &s->launches)); // stream-ordered before the launch that reads it
+			s->alphaKey[0] = p.invMu; s->alphaKey[1] = p.invLambda; s->alphaKey[2] = p.dt2;
+			s->alphaValid = true;
+		}
 		const uint32_t stride = plainSweep ? p.nColors + 1u : DataflowGeneralStride(p);
 		const uint32_t maxPerLaunch = std::max(1u, (0x00ffffffu - 2u) / stride); // tags of one launch must not wrap onto the stale ones
 		for (uint32_t done = 0; done < n;) {

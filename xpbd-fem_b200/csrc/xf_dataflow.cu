@@ -126,7 +126,7 @@ __device__ __forceinline__ bool ClusterElement(const DeviceScene& sc, const Subs
 			v[n].flags = r.flags;
 		}
 	}
-	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	const ElemCompliance ec = DataflowCompliance<EXACT>(sc, p, rec);
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll
@@ -263,7 +263,7 @@ __device__ __forceinline__ bool ChainElement(const DeviceScene& sc, const Subste
 	for (int n = 0; n < 4; n++) {
 		if (!first[n]) { v[n] = ChainLoad(cache, slot[n]); }
 	}
-	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	const ElemCompliance ec = DataflowCompliance<EXACT>(sc, p, rec);
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll

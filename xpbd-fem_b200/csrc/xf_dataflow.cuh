@@ -11,6 +11,15 @@ namespace xf {
 namespace {
 
 constexpr uint32_t kVerMask = 0xffffff00u;
+
+// alpha of the undamped solves: precomputed per element for the call's settings (DeviceScene::eAlpha, k_element_alpha).
+// Measured at 1M tets (profiles/r2_bench_alpha_plane_ab.log): 2.407 vs 2.510 ms per 50 substeps - the two chained IEEE divisions
+// with their slow-path checks were ~25 of ~700 instructions of every element, and the stage time follows the instruction count.
+template <bool EXACT>
+__device__ __forceinline__ ElemCompliance DataflowCompliance(const DeviceScene& sc, const SubstepParams& p, const ElemRec& rec) {
+	return ElemCompliance{ 0.0f, 0.0f, rec.alpha0, rec.alpha1 }; // comp0 / comp1 only feed in-constraint damping, which never runs here
+}
+
 // A record that never reaches the expected stage means a broken schedule (or a caller that rewrote the state while a
 // launch was in flight): report it (DeviceScene::errDev / errHost -> XF_ERR_CUDA from xf_sync and the getters) and drain the
 // kernel instead of hanging the device or trapping (a trap would poison the CUDA context of every scene of the process).
@@ -56,7 +65,7 @@ __device__ __forceinline__ bool DataflowElement(const DeviceScene& sc, const Sub
 	VertexRegs v[4];
 #pragma unroll
 	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(vid[n]); }
-	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume); // two chained divisions, in the shadow of the gather
+	const ElemCompliance ec = DataflowCompliance<EXACT>(sc, p, rec); // precomputed, or two chained divisions in the shadow of the gather
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll
@@ -86,6 +95,7 @@ template <int ENERGY, bool EXACT>
 __device__ __forceinline__ void DataflowPrefetch(const DeviceScene& sc, uint32_t e) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eAd + e));
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eAlpha + e));
 	asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eB + e));
 	if (kPrefactored && EXACT) { asm volatile("prefetch.global.L1 [%0];" ::"l"(sc.eC + e)); }
 }
@@ -94,6 +104,9 @@ template <int ENERGY, bool EXACT>
 __device__ __forceinline__ void DataflowLoad(const DeviceScene& sc, uint32_t e, ElemRec& rec) {
 	constexpr bool kPrefactored = (ENERGY == XF_ENERGY_MIXED_SEL || ENERGY == XF_ENERGY_YEOH_SKIN_FAST);
 	LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
+	const float2 al = __ldg(sc.eAlpha + e);
+	rec.alpha0 = al.x;
+	rec.alpha1 = al.y;
 }
 
 }  // namespace

@@ -62,7 +62,7 @@ __device__ __forceinline__ bool GeneralElement(const DeviceScene& sc, const Subs
 	VertexRegs v[4];
 #pragma unroll
 	for (int n = 0; n < 4; n++) { v[n] = vs.LoadX(vid[n]); }
-	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	const ElemCompliance ec = DataflowCompliance<EXACT>(sc, p, rec);
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll

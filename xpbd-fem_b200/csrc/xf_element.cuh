@@ -49,6 +49,7 @@ struct ElemRec {
 	float Qi[3][3]; // [col][row]
 	float volume;
 	float QQ[3], QR[3];
+	float alpha0, alpha1; // comp / dt^2 of the call's settings (DeviceScene::eAlpha), filled by the barrier-free kernels' loads
 };
 
 // 256-bit read-only load (element planes never change after upload).

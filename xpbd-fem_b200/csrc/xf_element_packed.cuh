@@ -74,29 +74,46 @@ __device__ __forceinline__ void SolvePrefactoredSimulPacked(const PARAMS& p, con
 	// prefactored I1 and its gradient, Fem.cpp:163-192
 	float U = 0.0f;
 	V3p g0[4];
+	const float s2[3] = { O::mul(2.0f, e.QQ[0]), O::mul(2.0f, e.QQ[1]), O::mul(2.0f, e.QQ[2]) };
 #pragma unroll
 	for (int i = 0; i < 3; i++) {
 		U = O::add(U, O::mul(e.QQ[i], Dot(P[i], P[i])));
-		g0[i] = Scale(O::mul(2.0f, e.QQ[i]), P[i]);
+		g0[i].xy = Mul2(Bc(s2[i]), P[i].xy);
 	}
 	U = O::add(U, O::mul(e.QR[0], Dot(P[0], P[1])));
-	g0[0] = AddV(g0[0], Scale(e.QR[0], P[1]));
-	g0[1] = AddV(g0[1], Scale(e.QR[0], P[0]));
+	g0[0].xy = Add2(g0[0].xy, Mul2(Bc(e.QR[0]), P[1].xy));
+	g0[1].xy = Add2(g0[1].xy, Mul2(Bc(e.QR[0]), P[0].xy));
 	U = O::add(U, O::mul(e.QR[1], Dot(P[0], P[2])));
-	g0[0] = AddV(g0[0], Scale(e.QR[1], P[2]));
-	g0[2] = AddV(g0[2], Scale(e.QR[1], P[0]));
+	g0[0].xy = Add2(g0[0].xy, Mul2(Bc(e.QR[1]), P[2].xy));
+	g0[2].xy = Add2(g0[2].xy, Mul2(Bc(e.QR[1]), P[0].xy));
 	U = O::add(U, O::mul(e.QR[2], Dot(P[1], P[2])));
-	g0[1] = AddV(g0[1], Scale(e.QR[2], P[2]));
-	g0[2] = AddV(g0[2], Scale(e.QR[2], P[1]));
+	g0[1].xy = Add2(g0[1].xy, Mul2(Bc(e.QR[2]), P[2].xy));
+	g0[2].xy = Add2(g0[2].xy, Mul2(Bc(e.QR[2]), P[1].xy));
+	{	// z components: g0[0].z = (2QQ0*P0z + QR0*P1z) + QR1*P2z, g0[1].z = (2QQ1*P1z + QR0*P0z) + QR2*P2z with the products of rows 0
+		// and 1 paired, g0[2].z = (2QQ2*P2z + QR1*P0z) + QR2*P1z with its two QR products paired
+		const float2 Z01 = make_float2(P[0].z, P[1].z);
+		const float2 T1 = Mul2(make_float2(s2[0], s2[1]), Z01);          // {2QQ0*P0z, 2QQ1*P1z}
+		const float2 T2 = Mul2(Bc(e.QR[0]), Z01);                        // {QR0*P0z, QR0*P1z}
+		const float2 T3 = Mul2(make_float2(e.QR[1], e.QR[2]), Bc(P[2].z)); // {QR1*P2z, QR2*P2z}
+		const float2 T4 = Mul2(make_float2(e.QR[1], e.QR[2]), Z01);      // {QR1*P0z, QR2*P1z}
+		g0[0].z = O::add(O::add(T1.x, T2.y), T3.x);
+		g0[1].z = O::add(O::add(T1.y, T2.x), T3.y);
+		g0[2].z = O::add(O::add(O::mul(s2[2], P[2].z), T4.x), T4.y);
+	}
 	{
 		const V3p zero = { make_float2(0.0f, 0.0f), 0.0f };
 		g0[3] = SubV(SubV(SubV(zero, g0[0]), g0[1]), g0[2]);
 	}
 	float U0 = U;
 	if (ENERGY == XF_ENERGY_YEOH_SKIN_FAST) { // Fem.cpp:525-531
+		// YeohEnergy = (C0*IM + (C1*IM)*IM) + ((C2*IM)*IM)*IM, YeohSlope = (C0 + (2C1)*IM) + ((3C2)*IM)*IM: the products that differ only
+		// in their constant run as pairs
 		const float IM = O::sub(U, 3.0f);
-		U0 = fmaxf(0.0001f, YeohEnergy<true>(IM));
-		const float gScale = YeohSlope<true>(IM);
+		const float C0 = 0.1095f, C1 = 14.95f, C2 = 4.595f;
+		const float2 A = Mul2(make_float2(C1, O::mul(2.0f, C1)), Bc(IM));                     // {C1*IM, (2C1)*IM}
+		const float2 B = Mul2(Mul2(make_float2(C2, O::mul(3.0f, C2)), Bc(IM)), Bc(IM));       // {(C2*IM)*IM, ((3C2)*IM)*IM}
+		U0 = fmaxf(0.0001f, O::add(O::add(O::mul(C0, IM), O::mul(A.x, IM)), O::mul(B.x, IM)));
+		const float gScale = O::add(O::add(C0, A.y), B.y);
 #pragma unroll
 		for (int n = 0; n < 4; n++) { g0[n] = Scale(gScale, g0[n]); }
 	}
@@ -158,7 +175,8 @@ __device__ __forceinline__ void SolvePrefactoredSimulPacked(const PARAMS& p, con
 		const float2 a = Mul2(g0[n].xy, Bc(l0)), b = Mul2(g1[n].xy, Bc(l1));
 		const float2 acc = make_float2(O::add(a.x, b.y), O::add(a.y, b.x));
 		const float2 dxy = Mul2(Bc(v[n].w), acc);
-		const float dz = O::mul(v[n].w, O::add(O::mul(l0, g0[n].z), O::mul(l1, g1[n].z)));
+		const float2 lz = Mul2(make_float2(g0[n].z, g1[n].z), make_float2(l0, l1)); // {l0*g0z, l1*g1z}
+		const float dz = O::mul(v[n].w, O::add(lz.x, lz.y));
 		v[n].x[0] = __dadd_rn(v[n].x[0], (double)dxy.x);
 		v[n].x[1] = __dadd_rn(v[n].x[1], (double)dxy.y);
 		v[n].x[2] = __dadd_rn(v[n].x[2], (double)dz);

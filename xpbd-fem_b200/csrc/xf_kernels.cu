@@ -188,6 +188,15 @@ __global__ void __launch_bounds__(256) k_element_volumes(const DeviceScene sc) {
 	sc.eScratch[s] = O::mul(1.0f / 6.0f, det);
 }
 
+// alpha plane of the barrier-free kernels (DeviceScene::eAlpha): ComplianceOf's operations, once per element and settings change
+template <bool EXACT>
+__global__ void __launch_bounds__(256) k_element_alpha(const DeviceScene sc, const __grid_constant__ SubstepParams p) {
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= sc.nT) { return; }
+	const ElemCompliance c = ComplianceOf<EXACT>(p, sc.eB[e].volume);
+	sc.eAlpha[e] = make_float2(c.alpha0, c.alpha1);
+}
+
 // Geo3d::Transform, Geo.cpp:358-364: positions narrowed to fp32, through the mat4, widened; O = X.
 __global__ void __launch_bounds__(256) k_transform(const DeviceScene sc, float c00, float c01, float c02, float c10, float c11, float c12, float c30,
                                                    float c31) {
@@ -424,6 +433,16 @@ cudaError_t LaunchPackState(const DeviceScene& sc, double* dX, double* dV, float
 cudaError_t LaunchUnpackState(const DeviceScene& sc, const double* dX, const double* dV, const float* dW, cudaStream_t stream,
                               uint64_t* launchCount) {
 	k_unpack_state<<<GridFor(sc.nV, 256), 256, 0, stream>>>(sc, dX, dV, dW);
+	++*launchCount;
+	return cudaGetLastError();
+}
+
+cudaError_t LaunchElementAlpha(const DeviceScene& sc, const SubstepParams& p, bool exact, cudaStream_t stream, uint64_t* launchCount) {
+	if (exact) {
+		k_element_alpha<true><<<GridFor(sc.nT, 256), 256, 0, stream>>>(sc, p);
+	} else {
+		k_element_alpha<false><<<GridFor(sc.nT, 256), 256, 0, stream>>>(sc, p);
+	}
 	++*launchCount;
 	return cudaGetLastError();
 }

@@ -382,7 +382,7 @@ __device__ __forceinline__ bool PartDataflowElement(const PartDevice& pd, const 
 		ackOk[n] = !needAck[n];
 	}
 	const uint32_t ackWant = stageBase & 0x00ffffffu;
-	const ElemCompliance ec = ComplianceOf<EXACT>(p, rec.volume);
+	const ElemCompliance ec = ElemCompliance{ 0.0f, 0.0f, rec.alpha0, rec.alpha1 }; // DeviceScene::eAlpha (undamped: comp unused)
 	for (uint32_t spins = 0;; spins++) {
 		bool ok[4];
 #pragma unroll
@@ -470,6 +470,9 @@ __global__ void __launch_bounds__(256, 2) k_part_dataflow(const __grid_constant_
 				if (has) {
 					ElemRec rec;
 					LoadElementFrom<kPrefactored, EXACT>(sc.eAd, sc, e, rec);
+					const float2 al = __ldg(sc.eAlpha + e); // alpha of this call's settings, k_element_alpha
+					rec.alpha0 = al.x;
+					rec.alpha1 = al.y;
 					dead = !PartDataflowElement<ENERGY, SIMUL, EXACT>(pd, p, rec, mask, ifacePool, stageBase, c);
 				}
 			}
@@ -591,6 +594,8 @@ struct xf_partition {
 	bool connected = false;
 	unsigned long long epoch = 0;
 	uint32_t verBase = 1; // first stage tag of the next barrier-free launch (24 bits, wraps; identical on all ranks)
+	float alphaKey[3] = { 0.0f, 0.0f, 0.0f }; // (invMu, invLambda, dt2) DeviceScene::eAlpha was computed for
+	bool alphaValid = false;
 	uint64_t launches = 0;
 	uint32_t groundOn = 0;
 	float groundY = 0.0f, groundFriction = 0.0f;
@@ -711,6 +716,7 @@ int UploadPart(xf_partition* P) {
 		}
 		XFP_CUDA(UploadVecP(&d.eAd, ad));
 		XFP_CUDA(UploadVecP(&d.lastCode, pl.lastCode));
+		XFP_CUDA(cudaMalloc((void**)&d.eAlpha, sizeof(float2) * std::max(nT, 1u)));
 	}
 	XFP_CUDA(cudaMalloc((void**)&P->dev.doneCounter, 2 * sizeof(unsigned int)));
 	XFP_CUDA(cudaMemset(P->dev.doneCounter, 0, 2 * sizeof(unsigned int)));
@@ -792,7 +798,7 @@ int xf_part_destroy(xf_partition* P) {
 		if (P->stream) { cudaStreamSynchronize(P->stream); }
 		for (void* p : P->openedPeers) { cudaIpcCloseMemHandle(p); }
 		DeviceScene& d = P->dev.local;
-		void* ptrs[] = { d.Xw, d.O, d.X0, d.eA, d.eB, d.eC, d.eArea, d.canonPos, d.eAd, d.lastCode, P->dSharedList, P->dPrivList, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
+		void* ptrs[] = { d.Xw, d.O, d.X0, d.eA, d.eB, d.eC, d.eArea, d.canonPos, d.eAd, d.lastCode, d.eAlpha, P->dSharedList, P->dPrivList, P->dShareStart, P->dShareSlot, P->dShareRemote, P->dColorStart, P->dIfaceEnd, P->dev.myFlags,
 			             P->dev.doneCounter, P->dPackX, P->dPackV, P->dPackW };
 		for (void* p : ptrs) { if (p) { cudaFree(p); } }
 		if (P->ownStream && P->stream) { cudaStreamDestroy(P->stream); }
@@ -931,6 +937,11 @@ int xf_part_substep(xf_partition* P, const xf_settings* st, float dt, uint32_t n
 		XFP_CUDA(DispatchConfig<PartRunner>(p.energy, p.simultaneous != 0, P->precision == XF_PRECISION_EXACT, inConstraint, P->dev, p, P->plan.colorStart,
 		                                    P->plan.ifaceEnd, P->mesh.colorStart, P->mesh.nT, n, &P->epoch, P->stream, &P->launches));
 	} else if (P->schedule == XF_SCHEDULE_DATAFLOW) {
+		if (!(P->alphaValid && P->alphaKey[0] == p.invMu && P->alphaKey[1] == p.invLambda && P->alphaKey[2] == p.dt2)) {
+			XFP_CUDA(LaunchElementAlpha(P->dev.local, p, P->precision == XF_PRECISION_EXACT, P->stream, &P->launches));
+			P->alphaKey[0] = p.invMu; P->alphaKey[1] = p.invLambda; P->alphaKey[2] = p.dt2;
+			P->alphaValid = true;
+		}
 		const uint32_t stride = P->dev.nColors + 1u;
 		const uint32_t maxPerLaunch = (0x00ffffffu - 2u) / stride;
 		for (uint32_t done = 0; done < n;) {

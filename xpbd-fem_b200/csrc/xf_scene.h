@@ -84,6 +84,11 @@ struct DeviceScene {
 	// (the amortised damping slices of Geo.cpp:794-797; byte 7 = the valence)
 	uint32_t* eRank = nullptr;
 	uint2* vSlice = nullptr;
+	// alpha = {1/mu/volume/dt^2, 1/lambda/volume/dt^2} per element (Fem.cpp:449, Xpbd.h:154) for the settings of the running call:
+	// two chained IEEE divisions per element and substep (~25 of ~700 instructions) that depend on (compliance, nu, dt) only, so
+	// k_element_alpha evaluates them once per change of those three - same operations, same bits - and the barrier-free kernels
+	// load 8 bytes instead
+	float2* eAlpha = nullptr;
 };
 
 // Threads per CTA of the barrier-free kernels.  Work is dealt one element per thread and colour, so only
@@ -237,6 +242,7 @@ cudaError_t LaunchSubstepsCluster(const DeviceScene& sc, const SubstepParams& p,
                                   uint32_t tuning, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchSubstepsPersistent(const DeviceScene& sc, const SubstepParams& p, bool exact, uint32_t nSubsteps, const LaunchShape& shape,
                                      cudaStream_t stream, uint64_t* launchCount);
+cudaError_t LaunchElementAlpha(const DeviceScene& sc, const SubstepParams& p, bool exact, cudaStream_t stream, uint64_t* launchCount);  // -> sc.eAlpha
 cudaError_t LaunchElementVolumes(const DeviceScene& sc, cudaStream_t stream, uint64_t* launchCount);  // -> sc.eScratch, stream order
 cudaError_t LaunchTransform(const DeviceScene& sc, const float* m9, cudaStream_t stream, uint64_t* launchCount);
 cudaError_t LaunchStats(const DeviceScene& sc, const SubstepParams& p, double gx, double gy, int smCount, cudaStream_t stream,
