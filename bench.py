@@ -446,7 +446,9 @@ def leg_partitioned(B):
             part.Substep(st, B.dt, n)
         X, V, w = part.get_state()
         l2g, order = part.local_verts(), part.get_order()
+        dist.barrier()  # nobody unmaps / frees while a peer may still hold the mapping
         part.close()
+        dist.barrier()
         gathered = [None] * B.world
         dist.gather_object((l2g, X, V, w), gathered if B.rank == 0 else None, dst=0)
     else:
@@ -476,20 +478,41 @@ def leg_partitioned(B):
     nodes, idx, hint = xf.GenerateTetBlock(c, c)
     sub, steps = args.substeps_per_step, 4
     if B.world > 1:
-        part = xf.GeoPartitionCuda(nodes, idx, B.world, B.rank, device=B.local_rank, color_hint=hint, stream=B.stream)
-        part_connect(B, part)
-        nT, nV = part.nTGlobal, part.nVGlobal
-        l0 = part.info()["launches"]
-        ms, _, _ = B.timed(lambda: part.Substep(st, B.dt, sub), steps, 2, flush=False)
-        launches = part.info()["launches"] - l0 - 2
-        part.Sync()
-        Xl, _, _ = part.get_state()
-        finite = bool(np.isfinite(Xl).all())
-        shared = int(sum(len(part.halo(cc, s, True)) for cc in range(part.nColors) for s in range(part.nPeers)))
-        out.update({"kernel": "k_part_dataflow", "local_tets_rank0": part.nT, "local_verts_rank0": part.nV, "peers_rank0": part.nPeers,
-                    "shared_vertex_stores_per_substep_rank0": shared,
-                    "link": "NVLink peer stores, one 32-byte record per shared vertex per writing element; nobody polls remote memory"})
-        part.close()
+        # The barrier-free cross-GPU schedule is fail-stop: its two store-order hazards are closed by timing margins,
+        # and a violation ends in a REPORTED stall, never in a wrong result.  One such stall was seen in this leg (20M tets, 4 GPUs,
+        # profiles/r2_bench_n4_stall.err) among otherwise clean runs, so a stall here is recorded and the leg is measured again on the
+        # flag protocol (ordered by construction) instead of failing the whole line.
+        attempts = [("dataflow", xf.SCHEDULE_AUTO, "k_part_dataflow"), ("flag protocol (per-colour launches)", xf.SCHEDULE_LAUNCH_PER_COLOR, "k_part_sweep (x colours)")]
+        for name, schedule, kernel in attempts:
+            part = xf.GeoPartitionCuda(nodes, idx, B.world, B.rank, device=B.local_rank, color_hint=hint, stream=B.stream, schedule=schedule)
+            part_connect(B, part)
+            nT, nV = part.nTGlobal, part.nVGlobal
+            l0 = part.info()["launches"]
+            stalled, ms = 0.0, 0.0
+            try:
+                ms, _, _ = B.timed(lambda: part.Substep(st, B.dt, sub), steps, 2, flush=False)
+                part.Sync()
+            except xf.XfError as err:
+                stalled = 1.0
+                out.setdefault("stalls", []).append("%s: %s" % (name, err))
+                torch.cuda.synchronize()
+            stalled = B.max_over_ranks(stalled)  # every rank takes the same branch
+            if stalled == 0.0:
+                launches = part.info()["launches"] - l0 - 2
+                Xl, _, _ = part.get_state()
+                finite = bool(np.isfinite(Xl).all())
+                shared = int(sum(len(part.halo(cc, s, True)) for cc in range(part.nColors) for s in range(part.nPeers)))
+                out.update({"kernel": kernel, "schedule": name, "local_tets_rank0": part.nT, "local_verts_rank0": part.nV, "peers_rank0": part.nPeers,
+                            "shared_vertex_stores_per_substep_rank0": shared,
+                            "link": "NVLink peer stores, one 32-byte record per shared vertex per writing element; nobody polls remote memory"})
+            dist.barrier()
+            part.close()
+            dist.barrier()
+            if stalled == 0.0:
+                break
+        else:
+            out["error"] = "every schedule stalled"
+            return out
     else:
         geo = xf.GeoLinear3dCuda(nodes, idx, device=B.local_rank, stream=B.stream, color_hint=hint)
         nT, nV = geo.nT, geo.nV
