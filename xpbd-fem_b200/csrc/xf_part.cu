@@ -55,6 +55,9 @@ struct PartDevice {
 	// barrier-free schedule: 1 = a system-scope fence between the peer store and the local store of a shared vertex (the hand-off
 	// to a same-rank successor is then a release/acquire chain by construction); 0 = program order of two relaxed stores only
 	uint32_t releaseStores;
+	// ... and a gap (ns) between the peer store and the local store of a shared vertex: widens the margin of hazard (a) (a
+	// same-rank successor overtaking our peer store) by that much, at the price of the same delay on the interface chain
+	uint32_t storeGapNs;
 };
 
 __device__ __forceinline__ unsigned long long LoadAcquireSys(const unsigned long long* p) {
@@ -332,6 +335,7 @@ struct VersionedMirrorStore {
 	uint32_t vid[4];
 	VertexRec* remote[4]; // the peer's copy of corner n, or nullptr
 	bool release;         // fence between the peer store and the local store (PartDevice::releaseStores)
+	uint32_t gapNs;       // PartDevice::storeGapNs
 	__device__ __forceinline__ VertexRegs LoadX(uint32_t i) const { return LoadVertexSys(base.Xw, i); }
 	__device__ __forceinline__ void StoreX(uint32_t i, const VertexRegs& v) const {
 		VertexRec* r = i == vid[0] ? remote[0] : (i == vid[1] ? remote[1] : (i == vid[2] ? remote[2] : remote[3]));
@@ -341,6 +345,7 @@ struct VersionedMirrorStore {
 			// local record and then stores to the same peer address is ordered after us by the memory model (fence + relaxed store
 			// = release; its poll + the fence it issues before ITS peer store = acquire), not just by the order the stores left.
 			if (release) { asm volatile("fence.acq_rel.sys;" ::: "memory"); }
+			if (gapNs) { __nanosleep(gapNs); }
 		}
 		StoreVertexSys(base.Xw, i, v);
 	}
@@ -361,6 +366,7 @@ __device__ __forceinline__ bool PartDataflowElement(const PartDevice& pd, const 
 	VersionedMirrorStore vs;
 	vs.base = StoreOf(pd.local);
 	vs.release = pd.releaseStores != 0;
+	vs.gapNs = pd.storeGapNs;
 #pragma unroll
 	for (int n = 0; n < 4; n++) {
 		vid[n] = raw[n] & 0x00ffffffu;
@@ -709,6 +715,8 @@ int UploadPart(xf_partition* P) {
 		// a property of the timing, not of the memory model, and fail-stop when violated.  Off by default; the knob documents it.
 		P->dev.releaseStores = 0;
 		if (const char* env = getenv("XF_PART_RELEASE")) { P->dev.releaseStores = (uint32_t)atoi(env); }
+		P->dev.storeGapNs = 0;
+		if (const char* env = getenv("XF_PART_STORE_GAP_NS")) { P->dev.storeGapNs = (uint32_t)atoi(env); }
 		if (!sharedList.empty()) { P->dev.nIfaceWarps = std::max(P->dev.nIfaceWarps, 1u); } // somebody must carry the interface
 		std::vector<ElemRecA> ad = pk.a;
 		for (size_t k = 0; k < ad.size(); k++) {
