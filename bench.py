@@ -256,7 +256,8 @@ def source_hash():
     """sha256/16 of the sources of the dominant kernel: ties profiles/r2_traffic.json (ncu capture) to the build that is measured."""
     import hashlib
     h = hashlib.sha256()
-    for name in ("xf_dataflow.cu", "xf_element.cuh", "xf_phase.cuh", "xf_scene.h", "xf_dispatch.cuh"):
+    for name in ("xf_dataflow.cu", "xf_dataflow.cuh", "xf_dataflow_general.cu", "xf_element.cuh", "xf_element_packed.cuh", "xf_phase.cuh", "xf_scene.h",
+                 "xf_dispatch.cuh"):
         with open(os.path.join(ROOT, "xpbd-fem_b200", "csrc", name), "rb") as f:
             h.update(f.read())
     return h.hexdigest()[:16]
@@ -490,6 +491,8 @@ def leg_partitioned(B):
             l0 = part.info()["launches"]
             stalled, ms = 0.0, 0.0
             try:
+                if os.environ.get("XF_BENCH_FAKE_STALL") and name == "dataflow":  # exercises the fallback path (tools/r2_final_fallback.sh)
+                    raise xf.XfError(xf.XF_ERR_CUDA, "fake stall (XF_BENCH_FAKE_STALL)")
                 ms, _, _ = B.timed(lambda: part.Substep(st, B.dt, sub), steps, 2, flush=False)
                 part.Sync()
             except xf.XfError as err:
