@@ -198,6 +198,9 @@ int xf_get_stage_codes(const xf_scene* scene, uint8_t* predCode4, uint8_t* lastC
  * 8 if the record is gathered from L2 (waiting for its stage tag) | 16 if it is scattered to L2 after the solve; all zero when
  * the scene is not chained.  outPermille = corner uses served from a slot, per 1000.  Either pointer may be NULL. */
 int xf_get_chain_info(const xf_scene* scene, uint32_t* info, uint32_t* outPermille);
+/* Codes of the count-versioned velocity records behind the barrier-free damping sweeps: rank4 = 4 per element
+ * in the serial order of xf_get_order, below8 = 8 per vertex (elements around it below each eighth of the serial order). */
+int xf_get_damping_codes(const xf_scene* scene, uint8_t* rank4, uint8_t* below8);
 int xf_get_elements(const xf_scene* scene, uint32_t* idx4, float* Qi9, float* QQ3, float* QR3, float* volume, float* surfaceArea);
 
 /* ---- stepping (Geo3d::Substep, Geo.cpp:305-356), n substeps with tickId advancing per substep ---- */

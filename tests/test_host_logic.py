@@ -302,3 +302,34 @@ def test_product_does_not_reference_the_oracle():
         if os.path.isfile(path) and path.endswith((".py", ".cpp", ".cu", ".cuh", ".h", "Makefile")):
             text = open(path, errors="ignore").read()
             assert "xpbd_oracle" not in text and "oracle/" not in text.replace("the oracle", ""), path
+
+
+@pytest.mark.parametrize("dims,wonk,pattern,hint", [((6, 3), 0.0, 0, True), ((5, 4), 0.3, 1, False)])
+def test_damping_sweep_write_counts_replay(dims, wonk, pattern, hint):
+    """CPU replay of the count-versioned velocity records (k_substeps_dataflow_general): for every amortisation slice, walking the
+    in-slice elements in serial order, each element must find exactly the count it expects on each corner's record in BOTH sweeps
+    (expected = sweep * inSlice(v) + rank - below(v)), and after the sweeps every record must hold what the next predict waits for."""
+    nodes, idx, h = xf.GenerateTetBlock(*dims, wonkiness=wonk, pattern=pattern)
+    geo = host_scene(nodes, idx, color_hint=h if hint else None)
+    order = geo.get_order()
+    tets = idx.reshape(-1, 5)[:, 1:][order]          # corners at every serial position
+    rank, below = geo.damping_codes()
+    nT, nV = geo.nT, geo.nV
+    valence = np.bincount(tets.reshape(-1), minlength=nV)
+    assert np.array_equal(below[:, 7], valence)
+    for k in list(range(8)) + [8]:                   # 8 = not amortised: the whole mesh
+        lo, hi = (nT * k // 8, nT * (k + 1) // 8) if k < 8 else (0, nT)
+        b = (below[:, k - 1].astype(np.int64) if 0 < k < 8 else np.zeros(nV, dtype=np.int64))
+        inside = (below[:, k].astype(np.int64) if k < 8 else below[:, 7].astype(np.int64)) - b
+        # the codes agree with a direct count
+        direct = np.bincount(tets[lo:hi].reshape(-1), minlength=nV)
+        assert np.array_equal(inside, direct)
+        count = np.zeros(nV, dtype=np.int64)         # what the post phase stores
+        for sweep in range(2):
+            for pos in range(lo, hi):
+                for j in range(4):
+                    v = tets[pos, j]
+                    assert count[v] == sweep * inside[v] + rank[pos, j] - b[v], (k, sweep, pos, j)
+                    count[v] += 1
+        assert np.array_equal(count, 2 * inside)     # the next predict's expectation
+    geo.close()

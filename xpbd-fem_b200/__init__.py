@@ -132,7 +132,7 @@ _lib = None
 
 EXPORTS = [
     "xf_last_error", "xf_device_count", "xf_default_create_params", "xf_generate_tet_block", "xf_create", "xf_destroy",
-    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_chain_info", "xf_get_elements", "xf_substep",
+    "xf_vert_count", "xf_element_count", "xf_color_count", "xf_get_order", "xf_get_colors", "xf_get_stage_codes", "xf_get_chain_info", "xf_get_damping_codes", "xf_get_elements", "xf_substep",
     "xf_substep_varying", "xf_sync", "xf_set_ground", "xf_set_handles", "xf_get_state", "xf_set_state", "xf_get_rest", "xf_get_origin",
     "xf_get_state_async", "xf_set_state_async", "xf_transform", "xf_volume", "xf_stats", "xf_get_info",
     "xf_frame_state_init", "xf_frame_update",
@@ -416,6 +416,14 @@ class GeoLinear3dCuda:
         last = np.empty(self.nV, dtype=np.uint8)
         _check(lib().xf_get_stage_codes(self._h, _vp(pred), _vp(last)))
         return pred, last
+
+    def damping_codes(self):
+        """(rank[nT, 4] in serial order, below[nV, 8]): the write-count codes of the barrier-free damping sweeps."""
+        rank = np.empty((self.nT, 4), dtype=np.uint8)
+        below = np.empty((self.nV, 8), dtype=np.uint8)
+        lib().xf_get_damping_codes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _check(lib().xf_get_damping_codes(self._h, _vp(rank), _vp(below)))
+        return rank, below
 
     def chain_info(self):
         """XF_GROUPING_CHAINS: slot / first / last word of every element (xf_get_order positions) and the per-mille of

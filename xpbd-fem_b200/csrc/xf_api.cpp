@@ -85,6 +85,12 @@ struct xf_scene {
 	volatile unsigned int* stallWord = nullptr; // pinned host word a barrier-free kernel sets when it gives up on a record
 };
 
+namespace xf {
+// xf_prepare.cpp: write-count codes of the damping sweeps on the barrier-free schedule (DeviceScene::eRank / vSlice); `idxOfPos` = the
+// four vertex ids of the element at every serial position
+void DampingCodes(uint32_t nT, uint32_t nV, const uint32_t* idxOfPos, std::vector<uint32_t>* rank, std::vector<uint64_t>* below);
+}
+
 namespace {
 
 void FreeDevice(xf_scene* s) {
@@ -179,19 +185,9 @@ int UploadScene(xf_scene* s) {
 			// damping sweeps on the barrier-free schedule (xf_dataflow_general.cu): V records are versioned by a write count.
 			// Rank of every element among the elements around each of its corners' vertices (serial order), and per vertex how
 			// many of those elements lie below each boundary nT*q/8 of the amortised damping slices (Geo.cpp:794-797).
-			std::vector<uint32_t> rank(m.nT, 0);
-			std::vector<uint8_t> seen(m.nV, 0);
-			std::vector<uint64_t> below(m.nV, 0);
-			uint32_t bound[XF_AMORTIZATION_PERIOD + 1];
-			for (uint32_t q = 0; q <= XF_AMORTIZATION_PERIOD; q++) { bound[q] = (uint32_t)(((uint64_t)m.nT * q) / XF_AMORTIZATION_PERIOD); }
-			for (uint32_t k = 0, q0 = 1; k < m.nT; k++) {
-				while (q0 < XF_AMORTIZATION_PERIOD && k >= bound[q0]) { q0++; } // first boundary above position k
-				for (int j = 0; j < 4; j++) {
-					const uint32_t v = devIdx[4 * (size_t)k + j];
-					rank[k] |= (uint32_t)seen[v]++ << (8 * j);
-					for (uint32_t q = q0; q <= XF_AMORTIZATION_PERIOD; q++) { below[v] += 1ull << (8 * (q - 1)); }
-				}
-			}
+			std::vector<uint32_t> rank;
+			std::vector<uint64_t> below;
+			DampingCodes(m.nT, m.nV, devIdx.data(), &rank, &below);
 			std::vector<uint2> slice(m.nV);
 			for (uint32_t v = 0; v < m.nV; v++) { slice[v] = make_uint2((uint32_t)below[v], (uint32_t)(below[v] >> 32)); }
 			XF_CUDA(Upload(&d.eRank, rank));
@@ -386,6 +382,21 @@ int xf_get_stage_codes(const xf_scene* s, uint8_t* predCode4, uint8_t* lastCode)
 	StageCodes(s->mesh, s->mesh.order, &pred, &last);
 	if (predCode4) { memcpy(predCode4, pred.data(), pred.size()); }
 	if (lastCode) { memcpy(lastCode, last.data(), last.size()); }
+	return XF_OK;
+}
+
+// Codes of the count-versioned velocity records (k_substeps_dataflow_general), in the caller's vertex numbering and the serial order
+// of xf_get_order: rank4[4*k + j] = rank of the element at serial position k among the elements around its corner j;
+// below8[8*v + q] = elements around vertex v whose serial position is below nT*(q+1)/8.  Host-only scenes answer too.
+int xf_get_damping_codes(const xf_scene* s, uint8_t* rank4, uint8_t* below8) {
+	if (!s) { return Fail(XF_ERR_INVALID, "null scene"); }
+	const HostMesh& m = s->mesh;
+	std::vector<uint32_t> idxOfPos(4 * (size_t)m.nT), rank;
+	std::vector<uint64_t> below;
+	for (uint32_t k = 0; k < m.nT; k++) { for (int j = 0; j < 4; j++) { idxOfPos[4 * (size_t)k + j] = m.idx[4 * (size_t)m.order[k] + j]; } }
+	DampingCodes(m.nT, m.nV, idxOfPos.data(), &rank, &below);
+	if (rank4) { for (uint32_t k = 0; k < m.nT; k++) { for (int j = 0; j < 4; j++) { rank4[4 * (size_t)k + j] = (uint8_t)(rank[k] >> (8 * j)); } } }
+	if (below8) { for (uint32_t v = 0; v < m.nV; v++) { for (int q = 0; q < 8; q++) { below8[8 * (size_t)v + q] = (uint8_t)(below[v] >> (8 * q)); } } }
 	return XF_OK;
 }
 

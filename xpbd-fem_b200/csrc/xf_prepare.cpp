@@ -417,6 +417,27 @@ int PrepareMesh(const float* nodeXYZ, uint32_t nodeFloatCount, const uint32_t* i
 	return XF_OK;
 }
 
+// Damping sweeps on the barrier-free schedule (xf_dataflow_general.cu): V records are versioned by a write count.  Rank of every element
+// (serial position k) among the elements around each of its corners' vertices, 4 x 8 bits, and per vertex how many of those elements lie
+// below each boundary nT*q/8, q = 1..8, of the amortised damping slices (Geo.cpp:794-797), 8 x 8 bits (byte 7 = the valence).
+void DampingCodes(uint32_t nT, uint32_t nV, const uint32_t* idxOfPos, std::vector<uint32_t>* rankOut, std::vector<uint64_t>* belowOut) {
+	std::vector<uint32_t>& rank = *rankOut;
+	std::vector<uint64_t>& below = *belowOut;
+	rank.assign(nT, 0);
+	below.assign(nV, 0);
+	std::vector<uint8_t> seen(nV, 0);
+	uint32_t bound[XF_AMORTIZATION_PERIOD + 1];
+	for (uint32_t q = 0; q <= XF_AMORTIZATION_PERIOD; q++) { bound[q] = (uint32_t)(((uint64_t)nT * q) / XF_AMORTIZATION_PERIOD); }
+	for (uint32_t k = 0, q0 = 1; k < nT; k++) {
+		while (q0 < XF_AMORTIZATION_PERIOD && k >= bound[q0]) { q0++; } // first boundary above position k
+		for (int j = 0; j < 4; j++) {
+			const uint32_t v = idxOfPos[4 * (size_t)k + j];
+			rank[k] |= (uint32_t)seen[v]++ << (8 * j);
+			for (uint32_t q = q0; q <= XF_AMORTIZATION_PERIOD; q++) { below[v] += 1ull << (8 * (q - 1)); }
+		}
+	}
+}
+
 void StageCodes(const HostMesh& m, const std::vector<uint32_t>& order, std::vector<uint8_t>* pred, std::vector<uint8_t>* last) {
 	pred->assign(4 * (size_t)m.nT, 0);
 	last->assign(m.nV, 0);
