@@ -22,9 +22,9 @@
 // 1.2 us of grid barrier + arrival skew + ~1 us element latency, 25 times per substep.  Here the only serialisation left
 // is the true data dependence: predecessor's store -> L2 -> my load.
 //
-// Covers the main sweep (all energies / solve modes, undamped in-constraint) + the fused vertex phase.  Volume passes,
-// damping sweeps and in-constraint Rayleigh damping (which reads O of other threads' vertices) run on
-// XF_SCHEDULE_PERSISTENT; xf_substep falls back per call.
+// Covers the main sweep (all energies / solve modes, undamped in-constraint) + the fused vertex phase.  Calls with volume passes or
+// post-solve damping sweeps run on k_substeps_dataflow_general (xf_dataflow_general.cu, same protocol); only in-constraint Rayleigh
+// damping (which reads O of other threads' vertices) runs on XF_SCHEDULE_PERSISTENT, per call.
 #include "xf_dataflow.cuh"
 
 namespace xf {
