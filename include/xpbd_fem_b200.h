@@ -377,6 +377,14 @@ int xf_debug_l2_bandwidth(int device, int mode, uint64_t bytes, uint32_t passes,
 /* cycles of (mode 0) one element solve of a lone warp, (mode 1) one record hand-off between two SMs, (mode 2) one dependent
  * 256-bit L2 load: the decomposition of a stage of the barrier-free sweep (xf_probe_latency.cu) */
 int xf_debug_stage_latency(int device, int mode, uint32_t iterations, double* outCycles);
+/* The warp-cooperative element solve (FOUR lanes per element, xf_element_coop.cuh) against the one-thread solve of the stepping
+ * kernels on the same gathered elements (MixedSel / YeohSkinFast, simultaneous, undamped): elemConsts = nElems x 16 floats {Qi[9]
+ * ([col][row]), volume, QQ[3], QR[3]} as xf_get_elements returns them, X = nElems x 12 doubles, w = nElems x 4, params4 = {1 + mu/lambda,
+ * 1/mu, 1/lambda, dt^2}.  out8 = {cycles per solve of a lone warp: one-thread, four-lane; element solves per second with warpsPerSm
+ * warps on every SM: one-thread, four-lane; doubles that differ between the variants after `iterations` chained solves, doubles
+ * compared; SM count, SM clock in kHz}; outXSingle / outXCoop (nElems x 12 doubles, or NULL) receive the final positions. */
+int xf_debug_coop_element(int device, int energy, const float* elemConsts, const double* X, const float* w, uint32_t nElems,
+                          const float* params4, uint32_t iterations, int warpsPerSm, double* out8, double* outXSingle, double* outXCoop);
 int xf_debug_torn_records(int device, int remoteDevice, uint32_t nRecords, uint32_t rounds, uint64_t* outReads, uint64_t* outTorn);
 int xf_debug_scene_knob(xf_scene* scene, int knob, uint32_t value);
 int xf_debug_barrier_us(int device, int variant, int blocksPerSm, int threads, uint32_t iterations, float* outUsPerBarrier);

@@ -148,6 +148,7 @@ EXPORTS = [
     "xf_part_get_initial", "xf_part_get_dataflow_codes", "xf_part_ipc_export", "xf_part_ipc_connect", "xf_part_set_ground", "xf_part_substep", "xf_part_sync",
     "xf_part_get_state", "xf_part_get_info",
     "xf_debug_l2_bandwidth", "xf_debug_stage_latency", "xf_debug_torn_records", "xf_debug_scene_knob", "xf_debug_barrier_us",
+    "xf_debug_coop_element",
 ]
 
 
@@ -278,6 +279,44 @@ def stage_latency(device=0, mode=0, iterations=2000):
     lib().xf_debug_stage_latency.argtypes = [C.c_int, C.c_int, C.c_uint32, C.POINTER(C.c_double)]
     _check(lib().xf_debug_stage_latency(device, mode, iterations, C.byref(out)))
     return out.value
+
+
+def substep_constants(compliance, poisson, dt):
+    """{a = 1 + mu/lambda, 1/mu, 1/lambda, dt^2} of a call, in fp32 with one rounding per operation, as FillSubstepParams
+    (xf_prepare.cpp) and Fem.cpp:445-449 compute them."""
+    f = np.float32
+    mu = f(1.0) / f(compliance)
+    with np.errstate(divide="ignore"):
+        lam = (f(2.0) * mu * f(poisson)) / (f(1.0) - f(2.0) * f(poisson))
+        a = f(1.0) + mu / lam
+        inv_lambda = f(1.0) / lam
+    return np.array([a, f(1.0) / mu, inv_lambda, f(dt) * f(dt)], dtype=np.float32)
+
+
+def gathered_elements(elements, X, w):
+    """Inputs of xf_debug_coop_element from xf_get_elements' dict and a state: (consts [nT,16], Xg [nT,12], wg [nT,4])."""
+    idx = elements["idx"].astype(np.int64)
+    consts = np.ascontiguousarray(np.concatenate([elements["Qi"], elements["volume"][:, None], elements["QQ"], elements["QR"]], axis=1),
+                                  dtype=np.float32)
+    Xg = np.ascontiguousarray(X[idx].reshape(idx.shape[0], 12), dtype=np.float64)
+    wg = np.ascontiguousarray(w[idx], dtype=np.float32)
+    return consts, Xg, wg
+
+
+def coop_element_probe(consts, Xg, wg, params4, energy=Energy_YeohSkinFast, iterations=200, warps_per_sm=8, device=0):
+    """Four-lanes-per-element solve against the one-thread solve on the same gathered elements; see xf_debug_coop_element."""
+    L = lib()
+    L.xf_debug_coop_element.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]
+    n = consts.shape[0]
+    assert consts.shape == (n, 16) and Xg.shape == (n, 12) and wg.shape == (n, 4)
+    out = np.zeros(8, dtype=np.float64)
+    xs, xc = np.empty((n, 12), np.float64), np.empty((n, 12), np.float64)
+    params4 = np.ascontiguousarray(params4, dtype=np.float32)
+    _check(L.xf_debug_coop_element(device, int(energy), _vp(consts), _vp(Xg), _vp(wg), n, _vp(params4), iterations, warps_per_sm, _vp(out),
+                                   _vp(xs), _vp(xc)))
+    return dict(cycles_single=out[0], cycles_coop=out[1], solves_per_s_single=out[2], solves_per_s_coop=out[3], mismatched=int(out[4]),
+                compared=int(out[5]), sm_count=int(out[6]), clock_khz=out[7], x_single=xs, x_coop=xc)
 
 
 def torn_records(device=0, remote_device=-1, n_records=1 << 16, rounds=2000):
