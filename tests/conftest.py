@@ -33,6 +33,6 @@ def coop_emu(tmp_path_factory):
     assert c.returncode == 0, c.stderr
     lib = C.CDLL(out)
     vp, f32, u32 = C.c_void_p, C.c_float, C.c_uint32
-    lib.coop_emu_sweep.argtypes = [C.c_int, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, u32]
+    lib.coop_emu_sweep.argtypes = [C.c_int, C.c_int, vp, vp, vp, vp, vp, f32, f32, f32, f32, vp, vp, vp, u32]
     lib.coop_emu_sweep.restype = C.c_int
     return lib

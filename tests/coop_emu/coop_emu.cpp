@@ -46,6 +46,7 @@ struct HostOps {
 	static float sub(float a, float b) { return a - b; }
 	static float rcp(float x) { return 1.0f / x; }
 	static float max(float a, float b) { return a > b ? a : b; } // fmaxf for non-NaN operands
+	static float sel(bool cond, float a, float b) { return cond ? a : b; }
 	static double dsub(double a, double b) { return a - b; }
 	static double dadd(double a, double b) { return a + b; }
 	static float d2f(double a) { return (float)a; }
@@ -84,8 +85,9 @@ struct Elem {
 }  // namespace
 
 // One Gauss-Seidel sweep over `order` (element ids) of the mesh {idx4, element constants}, every element solved by the four-lane
-// code; X (3 doubles per vertex) is updated in place.  energy: XF_ENERGY_MIXED_SEL or XF_ENERGY_YEOH_SKIN_FAST.
-extern "C" int coop_emu_sweep(int energy, const uint32_t* idx4, const float* Qi9, const float* QQ3, const float* QR3, const float* volume,
+// code; X (3 doubles per vertex) is updated in place.  energy: XF_ENERGY_MIXED_SEL or XF_ENERGY_YEOH_SKIN_FAST; x3Gathered: every
+// lane reads vertex 3 itself instead of receiving it from lane 3.
+extern "C" int coop_emu_sweep(int energy, int x3Gathered, const uint32_t* idx4, const float* Qi9, const float* QQ3, const float* QR3, const float* volume,
                               float a, float invMu, float invLambda, float dt2, double* X, const float* w, const uint32_t* order,
                               uint32_t nOrder) {
 	if (energy != XF_ENERGY_MIXED_SEL && energy != XF_ENERGY_YEOH_SKIN_FAST) { return 1; }
@@ -107,10 +109,21 @@ extern "C" int coop_emu_sweep(int energy, const uint32_t* idx4, const float* Qi9
 			const float alpha1 = (comp1 == 0.0f && dt2 > 0.0f) ? 0.0f : comp1 / dt2;
 			const uint32_t v = idx4[4 * (size_t)t + l];
 			double x[3] = { X[3 * (size_t)v], X[3 * (size_t)v + 1], X[3 * (size_t)v + 2] };
+			const uint32_t v3 = idx4[4 * (size_t)t + 3];
+			const double x3[3] = { X[3 * (size_t)v3], X[3 * (size_t)v3 + 1], X[3 * (size_t)v3 + 2] };
+			quad.bar.wait(); // every lane has read vertex 3 before lane 3 rewrites it
 			if (energy == XF_ENERGY_YEOH_SKIN_FAST) {
-				xf::SolvePrefactoredSimulCoop4<XF_ENERGY_YEOH_SKIN_FAST>(ln, a, e, alpha0, alpha1, x, w[v]);
+				if (x3Gathered) {
+					xf::SolvePrefactoredSimulCoop4<XF_ENERGY_YEOH_SKIN_FAST, true>(ln, a, e, alpha0, alpha1, x, w[v], x3);
+				} else {
+					xf::SolvePrefactoredSimulCoop4<XF_ENERGY_YEOH_SKIN_FAST, false>(ln, a, e, alpha0, alpha1, x, w[v], x3);
+				}
 			} else {
-				xf::SolvePrefactoredSimulCoop4<XF_ENERGY_MIXED_SEL>(ln, a, e, alpha0, alpha1, x, w[v]);
+				if (x3Gathered) {
+					xf::SolvePrefactoredSimulCoop4<XF_ENERGY_MIXED_SEL, true>(ln, a, e, alpha0, alpha1, x, w[v], x3);
+				} else {
+					xf::SolvePrefactoredSimulCoop4<XF_ENERGY_MIXED_SEL, false>(ln, a, e, alpha0, alpha1, x, w[v], x3);
+				}
 			}
 			X[3 * (size_t)v] = x[0]; X[3 * (size_t)v + 1] = x[1]; X[3 * (size_t)v + 2] = x[2];
 			quad.bar.wait(); // the next element gathers what this one scattered

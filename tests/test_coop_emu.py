@@ -21,7 +21,8 @@ def _ptr(a):
 
 @pytest.mark.parametrize("energy", [xf.Energy_MixedSel, xf.Energy_YeohSkinFast])
 @pytest.mark.parametrize("poisson", [0.5, 0.45])
-def test_four_lane_sweep_matches_reference_bit_for_bit(coop_emu, energy, poisson):
+@pytest.mark.parametrize("x3_gathered", [0, 1])
+def test_four_lane_sweep_matches_reference_bit_for_bit(coop_emu, energy, poisson, x3_gathered):
     nodes, idx, hint = xf.GenerateTetBlock(5, 4, wonkiness=0.3)
     geo = xf.GeoLinear3dCuda(nodes, idx, device=-1, color_hint=hint)  # host-only scene: init + colouring, no stepping
     el = geo.get_elements()
@@ -48,7 +49,7 @@ def test_four_lane_sweep_matches_reference_bit_for_bit(coop_emu, energy, poisson
 
     a, inv_mu, inv_lambda, dt2 = xf.substep_constants(compliance, poisson, dt)
     Xe = X.copy()
-    rc = coop_emu.coop_emu_sweep(int(energy), _ptr(el["idx"]), _ptr(el["Qi"]), _ptr(el["QQ"]), _ptr(el["QR"]), _ptr(el["volume"]),
+    rc = coop_emu.coop_emu_sweep(int(energy), x3_gathered, _ptr(el["idx"]), _ptr(el["Qi"]), _ptr(el["QQ"]), _ptr(el["QR"]), _ptr(el["volume"]),
                             a, inv_mu, inv_lambda, dt2, _ptr(Xe), _ptr(np.ascontiguousarray(w, dtype=np.float32)), _ptr(order), order.size)
     assert rc == 0
     assert not np.array_equal(Xe, X)                    # the sweep did something

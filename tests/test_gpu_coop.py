@@ -40,7 +40,7 @@ def test_four_lane_solve_on_the_device_matches_one_thread_solve_and_host_emulati
     Xe = np.ascontiguousarray(Xg.reshape(-1, 3).copy())
     own = np.arange(4 * n, dtype=np.uint32).reshape(n, 4)
     order = np.arange(n, dtype=np.uint32)
-    rc = coop_emu.coop_emu_sweep(int(energy), _ptr(own), _ptr(el["Qi"]), _ptr(el["QQ"]), _ptr(el["QR"]), _ptr(el["volume"]),
+    rc = coop_emu.coop_emu_sweep(int(energy), 0, _ptr(own), _ptr(el["Qi"]), _ptr(el["QQ"]), _ptr(el["QR"]), _ptr(el["volume"]),
                                  p4[0], p4[1], p4[2], p4[3], _ptr(Xe), _ptr(np.ascontiguousarray(wg.reshape(-1))), _ptr(order), n)
     assert rc == 0
     assert np.array_equal(Xe.reshape(n, 12), r["x_coop"])

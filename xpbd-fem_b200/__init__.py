@@ -303,17 +303,17 @@ def gathered_elements(elements, X, w):
     return consts, Xg, wg
 
 
-def coop_element_probe(consts, Xg, wg, params4, energy=Energy_YeohSkinFast, iterations=200, warps_per_sm=8, device=0):
+def coop_element_probe(consts, Xg, wg, params4, energy=Energy_YeohSkinFast, iterations=200, warps_per_sm=8, device=0, variant=0):
     """Four-lanes-per-element solve against the one-thread solve on the same gathered elements; see xf_debug_coop_element."""
     L = lib()
-    L.xf_debug_coop_element.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
+    L.xf_debug_coop_element.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_void_p]
     n = consts.shape[0]
     assert consts.shape == (n, 16) and Xg.shape == (n, 12) and wg.shape == (n, 4)
     out = np.zeros(8, dtype=np.float64)
     xs, xc = np.empty((n, 12), np.float64), np.empty((n, 12), np.float64)
     params4 = np.ascontiguousarray(params4, dtype=np.float32)
-    _check(L.xf_debug_coop_element(device, int(energy), _vp(consts), _vp(Xg), _vp(wg), n, _vp(params4), iterations, warps_per_sm, _vp(out),
+    _check(L.xf_debug_coop_element(device, int(energy), int(variant), _vp(consts), _vp(Xg), _vp(wg), n, _vp(params4), iterations, warps_per_sm, _vp(out),
                                    _vp(xs), _vp(xc)))
     return dict(cycles_single=out[0], cycles_coop=out[1], solves_per_s_single=out[2], solves_per_s_coop=out[3], mismatched=int(out[4]),
                 compared=int(out[5]), sm_count=int(out[6]), clock_khz=out[7], x_single=xs, x_coop=xc)

@@ -16,7 +16,7 @@
 //                    redundantly (a broadcast would cost a shuffle stage on the dependence chain and save no issue slot: all
 //                    four lanes of a quad issue together anyway)
 //
-// Exchanges per element: x3 broadcast (3 fp64 shuffles), all-gather of P (9), the two foreign columns of F for the cofactors (6,
+// Exchanges per element: x3 broadcast (3 fp64 shuffles; none if every lane gathered vertex 3 itself), all-gather of P (9), the two foreign columns of F for the cofactors (6,
 // per-lane source), J (1), the 4 x 3 transposition of g0 and g1 from component lanes to vertex lanes through shared memory (8
 // scalar stores, 2 x 128-bit loads per lane), all-gather of the 4 x 3 weighted dots (12).
 //
@@ -50,8 +50,12 @@ XF_COOP_FN float CoopDot3(float a0, float a1, float a2, float b0, float b1, floa
 
 // `x`, `w`: the calling lane's vertex record (lane n of the quad holds vertex n of the element); `x` is updated in place.
 // `e`: the element's constants (same in the four lanes); `a` = 1 + mu/lambda (Fem.cpp:447); `alpha0/1` = compliance / dt^2.
-template <int ENERGY, class L, class REC>
-XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, float alpha0, float alpha1, double (&x)[3], float w) {
+// X3_GATHERED: every lane also gathered vertex 3's position itself (`x3in`; a second 256-bit load per lane next to its own
+// record, in parallel with it) instead of receiving it from lane 3 - one shuffle stage less on the dependence chain.  After the
+// solve, `x3in` is stale in lanes 0..2 (lane 3 holds the updated vertex).
+template <int ENERGY, bool X3_GATHERED, class L, class REC>
+XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, float alpha0, float alpha1, double (&x)[3], float w,
+                                           const double (&x3in)[3]) {
 	typedef typename L::O O;
 	const int q = ln.q();
 	const int c = q < 2 ? q : 2; // component owned in the component-lane phase (lane 3 shadows lane 2, its results are not used)
@@ -61,7 +65,7 @@ XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, f
 	{
 		double x3[3];
 		XF_COOP_UNROLL
-		for (int k = 0; k < 3; k++) { x3[k] = ln.shfl(x[k], 3); }
+		for (int k = 0; k < 3; k++) { x3[k] = X3_GATHERED ? x3in[k] : ln.shfl(x[k], 3); }
 		XF_COOP_UNROLL
 		for (int k = 0; k < 3; k++) { Pown[k] = O::d2f(O::dsub(x[k], x3[k])); }
 	}
@@ -89,9 +93,10 @@ XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, f
 	}
 
 	// ---- component lanes: coordinate c of the three edges
-	const float pc0 = c == 0 ? P[0][0] : (c == 1 ? P[0][1] : P[0][2]);
-	const float pc1 = c == 0 ? P[1][0] : (c == 1 ? P[1][1] : P[1][2]);
-	const float pc2 = c == 0 ? P[2][0] : (c == 1 ? P[2][1] : P[2][2]);
+	// (selects, not branches: the compiler turned the plain ternaries into a divergent region on the dependence chain)
+	const float pc0 = O::sel(c == 0, P[0][0], O::sel(c == 1, P[0][1], P[0][2]));
+	const float pc1 = O::sel(c == 0, P[1][0], O::sel(c == 1, P[1][1], P[1][2]));
+	const float pc2 = O::sel(c == 0, P[2][0], O::sel(c == 1, P[2][1], P[2][2]));
 	// gradient of the prefactored I1, component c of g0[0..3] (Fem.cpp:171-191): g[i] = 2QQ_i P_i, then the pairs (0,1) (0,2) (1,2)
 	float g0c[4];
 	g0c[0] = O::add(O::add(O::mul(O::mul(2.0f, e.QQ[0]), pc0), O::mul(e.QR[0], pc1)), O::mul(e.QR[1], pc2));
@@ -127,7 +132,7 @@ XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, f
 	const float d = O::sub(J, a);
 	const float U1 = O::mul(d, d);            // Fem.cpp:537-540 (weight == 1)
 	const float s = O::mul(2.0f, d);
-	const float se = (c & 1) ? -s : s;        // scale of the cofactors with even first index
+	const float se = O::sel((c & 1) != 0, -s, s); // scale of the cofactors with even first index
 	const float G0 = O::mul(raw0, se), G1 = O::mul(raw1, -se), G2 = O::mul(raw2, se); // GJ[i][c]
 	// component c of g1[n] = (GJ[0][c]*Qi[n][0] + GJ[1][c]*Qi[n][1]) + GJ[2][c]*Qi[n][2], Fem.cpp:338-354
 	float g1c[4];
@@ -136,12 +141,11 @@ XF_COOP_FN void SolvePrefactoredSimulCoop4(const L& ln, float a, const REC& e, f
 	g1c[3] = O::sub(O::sub(O::sub(0.0f, g1c[0]), g1c[1]), g1c[2]);
 
 	// ---- component lanes -> vertex lanes: row n of the quad's shared memory = {g0[n][0..2], -, g1[n][0..2], -}
-	if (q < 3) {
-		XF_COOP_UNROLL
-		for (int n = 0; n < 4; n++) {
-			ln.sts(8 * n + q, g0c[n]);
-			ln.sts(8 * n + 4 + q, g1c[n]);
-		}
+	// (lane 3 writes its shadow values into the two padding columns: no divergence around the stores)
+	XF_COOP_UNROLL
+	for (int n = 0; n < 4; n++) {
+		ln.sts(8 * n + q, g0c[n]);
+		ln.sts(8 * n + 4 + q, g1c[n]);
 	}
 	ln.sync();
 	float g0v[3], g1v[3];
@@ -190,6 +194,15 @@ struct DevOps {
 	static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
 	static __device__ __forceinline__ float rcp(float x) { return __frcp_rn(x); }
 	static __device__ __forceinline__ float max(float a, float b) { return fmaxf(a, b); }
+	static __device__ __forceinline__ float sel(bool cond, float a, float b) {
+		float r;
+		asm("{ .reg .pred p;\n\t"
+		    "setp.ne.s32 p, %3, 0;\n\t"
+		    "selp.f32 %0, %1, %2, p; }"
+		    : "=f"(r)
+		    : "f"(a), "f"(b), "r"((int)cond));
+		return r;
+	}
 	static __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 	static __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
 	static __device__ __forceinline__ float d2f(double a) { return __double2float_rn(a); }

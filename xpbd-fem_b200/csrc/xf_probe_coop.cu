@@ -68,7 +68,10 @@ __global__ void __launch_bounds__(256) k_probe_single(const ProbeElem* elems, ui
 }
 
 // four lanes per element (thread t -> element (t / 4) mod nElems, vertex t mod 4)
-template <int ENERGY>
+// X3G: every lane also gathers vertex 3's position itself (xf_element_coop.cuh).  The probe gathers once, so in a chain of solves
+// lanes 0..2 keep the FIRST x3: the work and the dependence chain through a lane's own record are those of a sweep, where every
+// element gathers fresh records, but only the first solve of the chain is comparable with the one-thread variant.
+template <int ENERGY, bool X3G>
 __global__ void __launch_bounds__(256) k_probe_coop4(const ProbeElem* elems, uint32_t nElems, const double* X, const float* W, SubstepParams p,
                                                     uint32_t iters, double* out, long long* outCycles) {
 	__shared__ __align__(16) float sm[(256 / 4) * kCoopQuadFloats];
@@ -80,11 +83,16 @@ __global__ void __launch_bounds__(256) k_probe_coop4(const ProbeElem* elems, uin
 	double x[3];
 #pragma unroll
 	for (int k = 0; k < 3; k++) { x[k] = X[12 * (size_t)ei + 3 * lane4 + k]; }
+	double x3[3] = { 0.0, 0.0, 0.0 };
+	if (X3G) {
+#pragma unroll
+		for (int k = 0; k < 3; k++) { x3[k] = X[12 * (size_t)ei + 9 + k]; }
+	}
 	const float w = W[4 * (size_t)ei + lane4];
 	const ElemCompliance ec = ComplianceOf<true>(p, rec.volume);
 	const DevLane4 ln{ 0xffffffffu, lane4, sm + (threadIdx.x >> 2) * kCoopQuadFloats };
 	const long long t0 = clock64();
-	for (uint32_t k = 0; k < iters; k++) { SolvePrefactoredSimulCoop4<ENERGY>(ln, p.a, rec, ec.alpha0, ec.alpha1, x, w); }
+	for (uint32_t k = 0; k < iters; k++) { SolvePrefactoredSimulCoop4<ENERGY, X3G>(ln, p.a, rec, ec.alpha0, ec.alpha1, x, w, x3); }
 	const long long t1 = clock64();
 	if (out && quad < nElems) {
 #pragma unroll
@@ -94,15 +102,17 @@ __global__ void __launch_bounds__(256) k_probe_coop4(const ProbeElem* elems, uin
 }
 
 template <int ENERGY>
-void Launch(bool coop, int blocks, int threads, const ProbeElem* elems, uint32_t nElems, const double* X, const float* W, const SubstepParams& p,
+void Launch(int coop, int blocks, int threads, const ProbeElem* elems, uint32_t nElems, const double* X, const float* W, const SubstepParams& p,
             uint32_t iters, double* out, long long* cyc) {
-	if (coop) {
-		k_probe_coop4<ENERGY><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
+	if (coop == 2) {
+		k_probe_coop4<ENERGY, true><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
+	} else if (coop == 1) {
+		k_probe_coop4<ENERGY, false><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
 	} else {
 		k_probe_single<ENERGY><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
 	}
 }
-void LaunchE(int energy, bool coop, int blocks, int threads, const ProbeElem* elems, uint32_t nElems, const double* X, const float* W,
+void LaunchE(int energy, int coop, int blocks, int threads, const ProbeElem* elems, uint32_t nElems, const double* X, const float* W,
              const SubstepParams& p, uint32_t iters, double* out, long long* cyc) {
 	if (energy == (int)XF_ENERGY_YEOH_SKIN_FAST) {
 		Launch<XF_ENERGY_YEOH_SKIN_FAST>(coop, blocks, threads, elems, nElems, X, W, p, iters, out, cyc);
@@ -119,11 +129,17 @@ void LaunchE(int energy, bool coop, int blocks, int threads, const ProbeElem* el
 // out8 = {cycles per solve of a lone warp: one-thread, four-lane; element solves per second with warpsPerSm warps on every SM:
 //         one-thread, four-lane; doubles that differ between the variants after `iterations` chained solves, doubles compared;
 //         SM count, SM clock in kHz}.  outXSingle / outXCoop (optional): nElems x 12 doubles, the final positions of each variant.
-extern "C" int xf_debug_coop_element(int device, int energy, const float* elemConsts, const double* X, const float* w, uint32_t nElems,
-                                     const float* params4, uint32_t iterations, int warpsPerSm, double* out8, double* outXSingle,
-                                     double* outXCoop) {
+// variant 0: lane 3 broadcasts vertex 3; variant 1: every lane gathered vertex 3 itself (parity is then meaningful for
+// iterations == 1 only, see k_probe_coop4).
+extern "C" int xf_debug_coop_element(int device, int energy, int variant, const float* elemConsts, const double* X, const float* w,
+                                     uint32_t nElems, const float* params4, uint32_t iterations, int warpsPerSm, double* out8,
+                                     double* outXSingle, double* outXCoop) {
 	using namespace xf;
-	if (!elemConsts || !X || !w || !params4 || !out8 || nElems == 0 || iterations == 0 || warpsPerSm < 1 || warpsPerSm > 64) { return XF_ERR_INVALID; }
+	if (!elemConsts || !X || !w || !params4 || !out8 || nElems == 0 || iterations == 0 || warpsPerSm < 1 || warpsPerSm > 64 || variant < 0 ||
+	    variant > 1) {
+		return XF_ERR_INVALID;
+	}
+	const int coopKind = 1 + variant;
 	if (energy != (int)XF_ENERGY_YEOH_SKIN_FAST && energy != (int)XF_ENERGY_MIXED_SEL) { return XF_ERR_UNSUPPORTED; }
 	if (cudaSetDevice(device) != cudaSuccess) { return XF_ERR_CUDA; }
 	cudaDeviceProp prop;
@@ -160,8 +176,8 @@ extern "C" int xf_debug_coop_element(int device, int energy, const float* elemCo
 	std::vector<double> hS(nX), hC(nX);
 	if (rc == XF_OK) {
 		// ---- parity: every element, `iterations` chained solves, both variants
-		LaunchE(energy, false, (int)((nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutS, nullptr);
-		LaunchE(energy, true, (int)((4 * (size_t)nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutC, nullptr);
+		LaunchE(energy, 0, (int)((nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutS, nullptr);
+		LaunchE(energy, coopKind, (int)((4 * (size_t)nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutC, nullptr);
 		ok(cudaDeviceSynchronize());
 		ok(cudaMemcpy(hS.data(), dOutS, sizeof(double) * nX, cudaMemcpyDeviceToHost));
 		ok(cudaMemcpy(hC.data(), dOutC, sizeof(double) * nX, cudaMemcpyDeviceToHost));
@@ -174,8 +190,8 @@ extern "C" int xf_debug_coop_element(int device, int energy, const float* elemCo
 		if (outXSingle) { memcpy(outXSingle, hS.data(), sizeof(double) * nX); }
 		if (outXCoop) { memcpy(outXCoop, hC.data(), sizeof(double) * nX); }
 		// ---- latency: a lone warp
-		LaunchE(energy, false, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc);
-		LaunchE(energy, true, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc + 1);
+		LaunchE(energy, 0, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc);
+		LaunchE(energy, coopKind, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc + 1);
 		ok(cudaDeviceSynchronize());
 		long long cyc[2] = { 0, 0 };
 		ok(cudaMemcpy(cyc, dCyc, sizeof(cyc), cudaMemcpyDeviceToHost));
@@ -186,13 +202,13 @@ extern "C" int xf_debug_coop_element(int device, int energy, const float* elemCo
 		// ---- throughput: warpsPerSm warps on every SM (CTAs of up to 8 warps)
 		const int threads = warpsPerSm >= 8 ? 256 : warpsPerSm * 32;
 		const int blocks = prop.multiProcessorCount * (warpsPerSm >= 8 ? warpsPerSm / 8 : 1);
-		for (int variant = 0; variant < 2 && rc == XF_OK; variant++) {
-			const bool coop = variant == 1;
-			LaunchE(energy, coop, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr); // warm-up
+		for (int v = 0; v < 2 && rc == XF_OK; v++) {
+			const bool coop = v == 1;
+			LaunchE(energy, coop ? coopKind : 0, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr); // warm-up
 			float best = 0.0f;
 			for (int rep = 0; rep < 3; rep++) {
 				ok(cudaEventRecord(e0));
-				LaunchE(energy, coop, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr);
+				LaunchE(energy, coop ? coopKind : 0, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr);
 				ok(cudaEventRecord(e1));
 				ok(cudaEventSynchronize(e1));
 				float ms = 0.0f;
@@ -200,7 +216,7 @@ extern "C" int xf_debug_coop_element(int device, int energy, const float* elemCo
 				if (rep == 0 || ms < best) { best = ms; }
 			}
 			const double solves = (double)blocks * (double)threads / (coop ? 4.0 : 1.0) * (double)iterations;
-			out8[2 + variant] = best > 0.0f ? solves / ((double)best * 1e-3) : 0.0;
+			out8[2 + v] = best > 0.0f ? solves / ((double)best * 1e-3) : 0.0;
 		}
 		out8[6] = (double)prop.multiProcessorCount;
 		out8[7] = (double)clockKHz;
