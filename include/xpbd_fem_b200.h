@@ -383,8 +383,9 @@ int xf_debug_stage_latency(int device, int mode, uint32_t iterations, double* ou
  * 1/mu, 1/lambda, dt^2}.  out8 = {cycles per solve of a lone warp: one-thread, four-lane; element solves per second with warpsPerSm
  * warps on every SM: one-thread, four-lane; doubles that differ between the variants after `iterations` chained solves, doubles
  * compared; SM count, SM clock in kHz}; outXSingle / outXCoop (nElems x 12 doubles, or NULL) receive the final positions.
- * variant 0: lane 3 broadcasts vertex 3's position; 1: every lane gathered it itself (one shuffle stage less; the probe gathers
- * once, so the variants are comparable bit for bit for iterations == 1 only). */
+ * variant bit 0: 0 = lane 3 broadcasts vertex 3's position, 1 = every lane gathered it itself (one shuffle stage less; the probe
+ * gathers once, so the two sides are comparable bit for bit for iterations == 1 only); bit 1: the one-thread side runs the scalar
+ * arithmetic instead of the two-wide one (same bits). */
 int xf_debug_coop_element(int device, int energy, int variant, const float* elemConsts, const double* X, const float* w, uint32_t nElems,
                           const float* params4, uint32_t iterations, int warpsPerSm, double* out8, double* outXSingle, double* outXCoop);
 int xf_debug_torn_records(int device, int remoteDevice, uint32_t nRecords, uint32_t rounds, uint64_t* outReads, uint64_t* outTorn);

@@ -30,11 +30,13 @@ def test_four_lane_solve_on_the_device_matches_one_thread_solve_and_host_emulati
     consts, Xg, wg = xf.gathered_elements(el, X, w)
     p4 = xf.substep_constants(1.0, poisson, 1.0 / 3000.0)
     n = consts.shape[0]
-    for iterations in (1, 25):
-        r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=iterations, warps_per_sm=2)
+    # variant bit 0: every lane gathered vertex 3 itself (the probe gathers once: comparable for one solve only);
+    # bit 1: the one-thread side runs the scalar arithmetic instead of the two-wide one
+    for variant, iterations in ((0, 1), (0, 25), (2, 1), (2, 25), (1, 1), (3, 1)):
+        r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=iterations, warps_per_sm=2, variant=variant)
         assert r["compared"] == 12 * n
         assert not np.array_equal(r["x_single"], Xg)
-        assert r["mismatched"] == 0 and np.array_equal(r["x_coop"], r["x_single"])
+        assert r["mismatched"] == 0 and np.array_equal(r["x_coop"], r["x_single"]), (variant, iterations, r["mismatched"])
     # host emulation of the same header on the same (independent) elements, one solve each
     r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=1, warps_per_sm=1)
     Xe = np.ascontiguousarray(Xg.reshape(-1, 3).copy())

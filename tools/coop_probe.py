@@ -41,17 +41,19 @@ def main():
             run = {"energy": name, "poisson": poisson, "parity": [], "timing": []}
             # parity: variant 0 (lane 3 broadcasts vertex 3) on a short and a longer chain of solves; variant 1 (every lane gathered
             # vertex 3 itself) on one solve - the probe gathers once, so its chains are not comparable (xf_probe_coop.cu)
-            for variant, its in ((0, (1, 20)), (1, (1,))):
+            # variant 2: the one-thread side runs the scalar arithmetic (no two-wide instructions)
+            for variant, its in ((0, (1, 20)), (1, (1,)), (2, (1, 20))):
                 for it in its:
                     r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=it, warps_per_sm=1, variant=variant)
                     run["parity"].append({"variant": variant, "iterations": it, "mismatched_doubles": r["mismatched"],
                                           "compared_doubles": r["compared"], "moved": bool(not np.array_equal(r["x_single"], Xg)),
                                           "finite": bool(np.isfinite(r["x_coop"]).all())})
             if poisson == 0.5:
-                for variant in (0, 1):
-                    for wps in (1, 2, 4, 8, 16):
+                for variant in (0, 1, 2):
+                    for wps in ((1, 2, 4, 8, 16) if variant < 2 else (1, 4, 8, 16)):
                         r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=2000, warps_per_sm=wps, variant=variant)
                         run["timing"].append({"variant": variant, "warps_per_sm": wps, "iterations": 2000,
+                                              "one_thread_arithmetic": "scalar" if variant & 2 else "two-wide (what the kernels run)",
                                               "lone_warp_cycles_per_solve": {"one_thread": r["cycles_single"], "four_lane": r["cycles_coop"]},
                                               "element_solves_per_s": {"one_thread": r["solves_per_s_single"], "four_lane": r["solves_per_s_coop"]},
                                               "sm_count": r["sm_count"], "clock_khz": r["clock_khz"]})

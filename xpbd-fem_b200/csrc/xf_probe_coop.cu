@@ -38,8 +38,21 @@ __device__ __forceinline__ ElemRec LoadProbeElem(const ProbeElem* elems, uint32_
 	return r;
 }
 
-// one thread per element (thread t -> element t mod nElems)
+// The one-thread solve WITHOUT the two-wide arithmetic: the scalar branch of SolveElementGathered (xf_element.cuh), same bits.
 template <int ENERGY>
+__device__ __forceinline__ void SolveScalar(const SubstepParams& p, const ElemRec& e, VertexRegs (&v)[4], const ElemCompliance& ec) {
+	float P[3][3], F[3][3], g0[4][3], g1[4][3];
+	float U0;
+	bool haveF;
+	Edges<true>(v, P);
+	DeviatoricTerm<ENERGY, true>(e, P, U0, g0, F, haveF);
+	DeformationGradient<true>(e, P, F);
+	const float U1 = VolumetricFromF<true>(e, F, p.a, g1);
+	ConstrainBoth<true, false>(NoStore{}, p, e.idx, v, U0, U1, g0, g1, ec.comp0, ec.comp1, ec.alpha0, ec.alpha1, p.damping);
+}
+
+// one thread per element (thread t -> element t mod nElems); PACKED: the two-wide arithmetic the stepping kernels run
+template <int ENERGY, bool PACKED>
 __global__ void __launch_bounds__(256) k_probe_single(const ProbeElem* elems, uint32_t nElems, const double* X, const float* W, SubstepParams p,
                                                      uint32_t iters, double* out, long long* outCycles) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -55,7 +68,13 @@ __global__ void __launch_bounds__(256) k_probe_single(const ProbeElem* elems, ui
 	}
 	const ElemCompliance ec = ComplianceOf<true>(p, rec.volume);
 	const long long t0 = clock64();
-	for (uint32_t k = 0; k < iters; k++) { SolveElementGathered<ENERGY, true, true, false>(NoStore{}, p, rec, v, ec); }
+	for (uint32_t k = 0; k < iters; k++) {
+		if (PACKED) {
+			SolveElementGathered<ENERGY, true, true, false>(NoStore{}, p, rec, v, ec);
+		} else {
+			SolveScalar<ENERGY>(p, rec, v, ec);
+		}
+	}
 	const long long t1 = clock64();
 	if (out && t < nElems) {
 #pragma unroll
@@ -108,8 +127,10 @@ void Launch(int coop, int blocks, int threads, const ProbeElem* elems, uint32_t 
 		k_probe_coop4<ENERGY, true><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
 	} else if (coop == 1) {
 		k_probe_coop4<ENERGY, false><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
+	} else if (coop == 0) {
+		k_probe_single<ENERGY, true><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
 	} else {
-		k_probe_single<ENERGY><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
+		k_probe_single<ENERGY, false><<<blocks, threads>>>(elems, nElems, X, W, p, iters, out, cyc);
 	}
 }
 void LaunchE(int energy, int coop, int blocks, int threads, const ProbeElem* elems, uint32_t nElems, const double* X, const float* W,
@@ -129,17 +150,18 @@ void LaunchE(int energy, int coop, int blocks, int threads, const ProbeElem* ele
 // out8 = {cycles per solve of a lone warp: one-thread, four-lane; element solves per second with warpsPerSm warps on every SM:
 //         one-thread, four-lane; doubles that differ between the variants after `iterations` chained solves, doubles compared;
 //         SM count, SM clock in kHz}.  outXSingle / outXCoop (optional): nElems x 12 doubles, the final positions of each variant.
-// variant 0: lane 3 broadcasts vertex 3; variant 1: every lane gathered vertex 3 itself (parity is then meaningful for
-// iterations == 1 only, see k_probe_coop4).
+// variant bit 0: 0 = lane 3 broadcasts vertex 3, 1 = every lane gathered vertex 3 itself (parity is then meaningful for
+// iterations == 1 only, see k_probe_coop4); bit 1: the one-thread side runs the SCALAR arithmetic instead of the two-wide one.
 extern "C" int xf_debug_coop_element(int device, int energy, int variant, const float* elemConsts, const double* X, const float* w,
                                      uint32_t nElems, const float* params4, uint32_t iterations, int warpsPerSm, double* out8,
                                      double* outXSingle, double* outXCoop) {
 	using namespace xf;
 	if (!elemConsts || !X || !w || !params4 || !out8 || nElems == 0 || iterations == 0 || warpsPerSm < 1 || warpsPerSm > 64 || variant < 0 ||
-	    variant > 1) {
+	    variant > 3) {
 		return XF_ERR_INVALID;
 	}
-	const int coopKind = 1 + variant;
+	const int coopKind = 1 + (variant & 1);
+	const int singleKind = (variant & 2) ? -1 : 0;
 	if (energy != (int)XF_ENERGY_YEOH_SKIN_FAST && energy != (int)XF_ENERGY_MIXED_SEL) { return XF_ERR_UNSUPPORTED; }
 	if (cudaSetDevice(device) != cudaSuccess) { return XF_ERR_CUDA; }
 	cudaDeviceProp prop;
@@ -176,7 +198,7 @@ extern "C" int xf_debug_coop_element(int device, int energy, int variant, const 
 	std::vector<double> hS(nX), hC(nX);
 	if (rc == XF_OK) {
 		// ---- parity: every element, `iterations` chained solves, both variants
-		LaunchE(energy, 0, (int)((nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutS, nullptr);
+		LaunchE(energy, singleKind, (int)((nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutS, nullptr);
 		LaunchE(energy, coopKind, (int)((4 * (size_t)nElems + 255) / 256), 256, dE, nElems, dX, dW, p, iterations, dOutC, nullptr);
 		ok(cudaDeviceSynchronize());
 		ok(cudaMemcpy(hS.data(), dOutS, sizeof(double) * nX, cudaMemcpyDeviceToHost));
@@ -190,7 +212,7 @@ extern "C" int xf_debug_coop_element(int device, int energy, int variant, const 
 		if (outXSingle) { memcpy(outXSingle, hS.data(), sizeof(double) * nX); }
 		if (outXCoop) { memcpy(outXCoop, hC.data(), sizeof(double) * nX); }
 		// ---- latency: a lone warp
-		LaunchE(energy, 0, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc);
+		LaunchE(energy, singleKind, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc);
 		LaunchE(energy, coopKind, 1, 32, dE, nElems, dX, dW, p, iterations, nullptr, dCyc + 1);
 		ok(cudaDeviceSynchronize());
 		long long cyc[2] = { 0, 0 };
@@ -204,11 +226,11 @@ extern "C" int xf_debug_coop_element(int device, int energy, int variant, const 
 		const int blocks = prop.multiProcessorCount * (warpsPerSm >= 8 ? warpsPerSm / 8 : 1);
 		for (int v = 0; v < 2 && rc == XF_OK; v++) {
 			const bool coop = v == 1;
-			LaunchE(energy, coop ? coopKind : 0, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr); // warm-up
+			LaunchE(energy, coop ? coopKind : singleKind, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr); // warm-up
 			float best = 0.0f;
 			for (int rep = 0; rep < 3; rep++) {
 				ok(cudaEventRecord(e0));
-				LaunchE(energy, coop ? coopKind : 0, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr);
+				LaunchE(energy, coop ? coopKind : singleKind, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr);
 				ok(cudaEventRecord(e1));
 				ok(cudaEventSynchronize(e1));
 				float ms = 0.0f;
