@@ -485,7 +485,10 @@ def leg_partitioned(B):
         # and a violation ends in a REPORTED stall, never in a wrong result.  One such stall was seen in this leg (20M tets, 4 GPUs,
         # profiles/r2_bench_n4_stall.err) among otherwise clean runs, so a stall here is recorded and the leg is measured again on the
         # flag protocol (ordered by construction) instead of failing the whole line.
-        attempts = [("dataflow", xf.SCHEDULE_AUTO, "k_part_dataflow"), ("flag protocol (per-colour launches)", xf.SCHEDULE_LAUNCH_PER_COLOR, "k_part_sweep (x colours)")]
+        # The stalls are intermittent (3 of ~14 runs at 20M tets), so the barrier-free schedule gets ONE more attempt on a fresh partition
+        # before the fallback; every stall stays in `stalls` whatever is measured in the end.
+        attempts = [("dataflow", xf.SCHEDULE_AUTO, "k_part_dataflow"), ("dataflow (second attempt)", xf.SCHEDULE_AUTO, "k_part_dataflow"),
+                    ("flag protocol (per-colour launches)", xf.SCHEDULE_LAUNCH_PER_COLOR, "k_part_sweep (x colours)")]
         for name, schedule, kernel in attempts:
             part = xf.GeoPartitionCuda(nodes, idx, B.world, B.rank, device=B.local_rank, color_hint=hint, stream=B.stream, schedule=schedule)
             part_connect(B, part)
