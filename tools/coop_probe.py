@@ -50,7 +50,7 @@ def main():
                                           "finite": bool(np.isfinite(r["x_coop"]).all())})
             if poisson == 0.5:
                 for variant in (0, 1, 2):
-                    for wps in ((1, 2, 4, 8, 16) if variant < 2 else (1, 4, 8, 16)):
+                    for wps in ((1, 2, 4, 8, 12, 16) if variant < 2 else (4, 8, 12, 16)):
                         r = xf.coop_element_probe(consts, Xg, wg, p4, energy=energy, iterations=2000, warps_per_sm=wps, variant=variant)
                         run["timing"].append({"variant": variant, "warps_per_sm": wps, "iterations": 2000,
                                               "one_thread_arithmetic": "scalar" if variant & 2 else "two-wide (what the kernels run)",

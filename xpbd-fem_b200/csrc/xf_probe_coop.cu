@@ -160,6 +160,7 @@ extern "C" int xf_debug_coop_element(int device, int energy, int variant, const 
 	    variant > 3) {
 		return XF_ERR_INVALID;
 	}
+	if (warpsPerSm > 8 && warpsPerSm % 4 != 0) { return XF_ERR_INVALID; } // one CTA of <= 8 warps, or CTAs of 4 warps
 	const int coopKind = 1 + (variant & 1);
 	const int singleKind = (variant & 2) ? -1 : 0;
 	if (energy != (int)XF_ENERGY_YEOH_SKIN_FAST && energy != (int)XF_ENERGY_MIXED_SEL) { return XF_ERR_UNSUPPORTED; }
@@ -221,9 +222,11 @@ extern "C" int xf_debug_coop_element(int device, int energy, int variant, const 
 		out8[1] = (double)cyc[1] / (double)iterations;
 	}
 	if (rc == XF_OK) {
-		// ---- throughput: warpsPerSm warps on every SM (CTAs of up to 8 warps)
-		const int threads = warpsPerSm >= 8 ? 256 : warpsPerSm * 32;
-		const int blocks = prop.multiProcessorCount * (warpsPerSm >= 8 ? warpsPerSm / 8 : 1);
+		// ---- throughput: warpsPerSm warps on every SM: CTAs of 4 warps (one per scheduler) when warpsPerSm is a multiple of 4,
+		// else one CTA of warpsPerSm warps per SM
+		const bool quads = warpsPerSm % 4 == 0;
+		const int threads = quads ? 128 : warpsPerSm * 32;
+		const int blocks = prop.multiProcessorCount * (quads ? warpsPerSm / 4 : 1);
 		for (int v = 0; v < 2 && rc == XF_OK; v++) {
 			const bool coop = v == 1;
 			LaunchE(energy, coop ? coopKind : singleKind, blocks, threads, dE, nElems, dX, dW, p, iterations, nullptr, nullptr); // warm-up
